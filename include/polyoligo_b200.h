@@ -1,0 +1,158 @@
+/*
+ * polyoligo_b200.h -- C ABI of the B200 (sm_100a) thermodynamic scoring library.
+ *
+ * This is the drop-in boundary for the one hot path of MirkoLedda/polyoligo:
+ * batch nearest-neighbour Tm and primer3-style `thal` (hairpin / homodimer /
+ * heterodimer) evaluation, the KASP allele-specific candidate enumeration that
+ * feeds it and the validity filter / heterodimer check / goodness score /
+ * per-marker top-n that consume it.  Each entry point names the reference call
+ * (file:line under the reference tree) it replaces.  The reference reaches the
+ * arithmetic through primer3-py 0.6.0 (Cython -> libprimer3); a maintainer
+ * binds this library with ctypes instead.
+ *
+ * Conventions: every function returns 0 on success or a PO_E_* code; the
+ * message of the last failure is available from po_last_error().  The caller
+ * owns every buffer passed in; the library owns device memory inside po_ctx.
+ * No torch types, no C++ types.  One po_ctx per process and GPU.
+ */
+#ifndef POLYOLIGO_B200_H
+#define POLYOLIGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PO_MAX_OLIGO_LEN 60 /* thal.c THAL_MAX_ALIGN; also the 2-bit record capacity */
+
+enum {
+    PO_OK = 0,
+    PO_E_INVALID = 1, /* bad argument                                         */
+    PO_E_CUDA = 2,    /* CUDA runtime failure (message has the CUDA string)   */
+    PO_E_PARAMS = 3,  /* thermodynamic parameter files missing / malformed    */
+    PO_E_NOMEM = 4
+};
+
+/* thal alignment types (libprimer3 thal.h thal_alignment_type) */
+enum { PO_THAL_ANY = 1, PO_THAL_END1 = 2, PO_THAL_END2 = 3, PO_THAL_HAIRPIN = 4 };
+
+/* One oligo, 16 bytes, self-contained and vector-loadable:
+ *   bits 0..119  2-bit bases, base k at bits 2k..2k+1 (A=0 C=1 G=2 T=3)
+ *   byte 15      bits 0..5 length (0..60), bit 6 = invalid character seen,
+ *                bit 7 = contains N (or any other non-ACGT IUPAC letter)
+ * Oligos with bit 6/7 set or longer than 60 nt are not evaluated: their results
+ * carry PO_ITEM_SKIPPED.  (The reference rejects every N-containing primer
+ * regardless of its thermodynamics, reference src/polyoligo/lib_primer3.py:72-74.) */
+typedef struct {
+    uint32_t w[4];
+} po_oligo;
+
+#define PO_OLIGO_HAS_N 0x80u
+#define PO_OLIGO_BAD_CHAR 0x40u
+#define PO_OLIGO_LEN_MASK 0x3Fu
+
+/* Result of one thal evaluation (40 bytes).  Units follow primer3-py's
+ * ThermoResult: tm in deg C, dg and dh in cal/mol, ds in cal/(mol K). */
+typedef struct {
+    double tm; /* 0.0 when no structure was found (libprimer3 convention)   */
+    double dg;
+    double dh;
+    double ds;
+    int32_t flags;     /* PO_ITEM_* bits                                      */
+    int16_t align_end_1;
+    int16_t align_end_2;
+} po_thal_out;
+
+#define PO_ITEM_STRUCTURE_FOUND 0x1
+#define PO_ITEM_SKIPPED 0x2   /* empty / too long / non-ACGT input             */
+#define PO_ITEM_SYMMETRIC 0x4 /* both strands self-complementary (RC used 1e9) */
+
+/* Per-oligo properties computed by po_oligo_props_batch: the quantities
+ * Primer.calc_thermals gathers (reference src/polyoligo/lib_primer3.py:56-64). */
+typedef struct {
+    double tm;           /* calcTm                                            */
+    double hairpin_tm;   /* calcHairpin(seq).tm                               */
+    double homodimer_tm; /* calcHomodimer(seq).tm                             */
+    double gc_content;   /* Bio.SeqUtils.GC: 100 * (G + C) / len              */
+    int32_t length;
+    int32_t flags;       /* PO_ITEM_SKIPPED, PO_PRIMER_VALID                  */
+} po_oligo_props;
+
+#define PO_PRIMER_VALID 0x100 /* Primer.is_valid() (lib_primer3.py:66-97) passed */
+
+/* Thresholds of Primer.is_valid: PRIMER3_GLOBALS values from the assay YAML
+ * (reference src/polyoligo/data/PRIMER3_KASP.yaml) plus the CLI's tm_delta. */
+typedef struct {
+    int32_t min_size, max_size; /* PRIMER_MIN_SIZE / PRIMER_MAX_SIZE          */
+    double min_gc, max_gc;      /* PRIMER_MIN_GC / PRIMER_MAX_GC               */
+    double min_tm, max_tm;      /* PRIMER_MIN_TM / PRIMER_MAX_TM               */
+    double tm_delta;            /* lib_primer3.TM_DELTA (cli_kasp.py --tm_delta) */
+} po_valid_params;
+
+typedef struct po_ctx po_ctx;
+
+/* ---- lifetime ------------------------------------------------------------ */
+/* Creates the context on CUDA device `device`.  param_dir: directory in the
+ * libprimer3 primer3_config format (stack.ds ... tetraloop.dh) or NULL for the
+ * compiled-in default set.  Replaces: ThermoAnalysis() construction,
+ * reference src/polyoligo/lib_primer3.py:58,157; _lib_kasp.py:99. */
+int po_init(int device, const char *param_dir, po_ctx **out);
+void po_destroy(po_ctx *ctx);
+/* ctx may be NULL: returns the message of the last failed po_init. */
+const char *po_last_error(const po_ctx *ctx);
+
+/* ThermoAnalysis attributes mv_conc, dv_conc, dntp_conc, dna_conc, temp_c,
+ * max_loop, max_nn_length (defaults 50, 0, 0.8, 50, 37, 30, 60: the reference
+ * never changes them). */
+int po_set_conditions(po_ctx *ctx, double mv, double dv, double dntp, double dna_nM,
+                      double temp_c, int max_loop, int max_nn_length);
+
+/* ---- packing (host, no GPU needed) --------------------------------------- */
+/* n ASCII sequences stored back to back in `ascii`, item k = bytes
+ * [offsets[k], offsets[k+1]).  Case-insensitive. */
+int po_pack(const char *ascii, const int64_t *offsets, int64_t n, po_oligo *packed);
+/* Inverse; out must hold 61 bytes per item (NUL terminated, stride 61). */
+int po_unpack(const po_oligo *packed, int64_t n, char *out);
+
+/* ---- scoring, HOST buffers (copies are inside the call) ------------------- */
+/* calcTm for n oligos (lib_primer3.py:59, _lib_crispr.py:42).  gc may be NULL. */
+int po_tm_batch(po_ctx *ctx, const po_oligo *oligos, int64_t n, double *tm, double *gc);
+
+/* thal for n (a[k], b[k]) pairs.  type ANY with b == NULL is calcHomodimer
+ * (lib_primer3.py:61); with b it is calcHeterodimer (lib_primer3.py:158,
+ * _lib_kasp.py:100-105); type HAIRPIN ignores b (calcHairpin, lib_primer3.py:60). */
+int po_thal_batch(po_ctx *ctx, int type, const po_oligo *a, const po_oligo *b, int64_t n,
+                  po_thal_out *out);
+
+/* Primer.calc_thermals + Primer.is_valid for n oligos (lib_primer3.py:56-97).
+ * valid may be NULL (no validity bit is computed). */
+int po_oligo_props_batch(po_ctx *ctx, const po_oligo *oligos, int64_t n,
+                         const po_valid_params *valid, po_oligo_props *out);
+
+/* ---- scoring, DEVICE buffers (no copies; asynchronous on `stream`) -------- */
+/* Pointers are CUDA device pointers; stream is a cudaStream_t (NULL = the
+ * context's own stream).  The call returns after enqueueing. */
+int po_tm_batch_dev(po_ctx *ctx, const void *d_oligos, int64_t n, void *d_tm, void *d_gc,
+                    void *stream);
+int po_thal_batch_dev(po_ctx *ctx, int type, const void *d_a, const void *d_b, int64_t n,
+                      void *d_out, void *stream);
+/* Blocks until everything enqueued on `stream` (NULL = context stream) is done. */
+int po_sync(po_ctx *ctx, void *stream);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* Number of kernels this context has launched since po_init. */
+int64_t po_launch_count(const po_ctx *ctx);
+/* DP relaxations (SURVEY 8d work unit, counted exactly as the upstream
+ * algorithm performs them) of one po_thal_batch over host buffers; runs the
+ * instrumented kernel variant, not for timing. */
+int po_thal_count_relaxations(po_ctx *ctx, int type, const po_oligo *a, const po_oligo *b,
+                              int64_t n, int64_t *relaxations);
+/* Register-resident FP64 FMA microbenchmark: measured non-tensor FP64 peak of
+ * the device in TFLOP/s (the compute-roofline denominator). */
+int po_measure_fp64_peak(po_ctx *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

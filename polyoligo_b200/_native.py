@@ -1,0 +1,197 @@
+"""ctypes binding of libpolyoligo_b200.so (C ABI in include/polyoligo_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing or no context can be
+created the calls raise.  Packing (``pack`` / ``unpack``) is host-only and
+works without a GPU.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpolyoligo_b200.so")
+
+THAL_ANY, THAL_END1, THAL_END2, THAL_HAIRPIN = 1, 2, 3, 4
+ITEM_STRUCTURE_FOUND, ITEM_SKIPPED, ITEM_SYMMETRIC, PRIMER_VALID = 0x1, 0x2, 0x4, 0x100
+MAX_OLIGO_LEN = 60
+
+OLIGO_DTYPE = np.dtype([("w", "<u4", (4,))])
+THAL_OUT_DTYPE = np.dtype([("tm", "<f8"), ("dg", "<f8"), ("dh", "<f8"), ("ds", "<f8"),
+                           ("flags", "<i4"), ("align_end_1", "<i2"), ("align_end_2", "<i2")])
+PROPS_DTYPE = np.dtype([("tm", "<f8"), ("hairpin_tm", "<f8"), ("homodimer_tm", "<f8"),
+                        ("gc_content", "<f8"), ("length", "<i4"), ("flags", "<i4")])
+assert OLIGO_DTYPE.itemsize == 16 and THAL_OUT_DTYPE.itemsize == 40 and PROPS_DTYPE.itemsize == 40
+
+
+class ValidParams(C.Structure):
+    _fields_ = [("min_size", C.c_int32), ("max_size", C.c_int32),
+                ("min_gc", C.c_double), ("max_gc", C.c_double),
+                ("min_tm", C.c_double), ("max_tm", C.c_double),
+                ("tm_delta", C.c_double)]
+
+
+# every symbol include/polyoligo_b200.h declares
+EXPORTS = {
+    "po_init": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "po_destroy": (None, [C.c_void_p]),
+    "po_last_error": (C.c_char_p, [C.c_void_p]),
+    "po_set_conditions": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double,
+                                    C.c_double, C.c_int, C.c_int]),
+    "po_pack": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "po_unpack": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    "po_tm_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "po_thal_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "po_oligo_props_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "po_tm_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "po_thal_batch_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p]),
+    "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "po_launch_count": (C.c_int64, [C.c_void_p]),
+    "po_thal_count_relaxations": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                            C.POINTER(C.c_int64)]),
+    "po_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (building it is __graft_entry__.build()'s job)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "polyoligo_b200: %s is missing -- run `python -m polyoligo_b200.build` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _seq_blob(seqs):
+    if isinstance(seqs, tuple):
+        blob, off = seqs
+        return np.ascontiguousarray(blob, dtype=np.uint8), np.ascontiguousarray(off, dtype=np.int64)
+    off = np.zeros(len(seqs) + 1, dtype=np.int64)
+    if len(seqs):
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+    blob = np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8)
+    return blob, off
+
+
+def pack(seqs):
+    """list[str] (or (uint8 blob, int64 offsets)) -> structured array of 16-byte oligo records."""
+    blob, off = _seq_blob(seqs)
+    n = len(off) - 1
+    out = np.zeros(n, dtype=OLIGO_DTYPE)
+    buf = blob.tobytes() if blob.size else b""
+    rc = load().po_pack(buf, off.ctypes.data, n, out.ctypes.data)
+    if rc:
+        raise RuntimeError("po_pack failed (%d)" % rc)
+    return out
+
+
+def unpack(oligos):
+    oligos = np.ascontiguousarray(oligos, dtype=OLIGO_DTYPE)
+    n = len(oligos)
+    buf = np.zeros(61 * n, dtype=np.uint8)
+    rc = load().po_unpack(oligos.ctypes.data, n, buf.ctypes.data)
+    if rc:
+        raise RuntimeError("po_unpack failed (%d)" % rc)
+    raw = buf.reshape(n, 61)
+    return [bytes(r[:int(np.argmax(r == 0))]).decode("ascii") for r in raw]
+
+
+class Context:
+    """One CUDA context of the scoring library on one GPU."""
+
+    def __init__(self, device=0, param_dir=None):
+        lib = load()
+        h = C.c_void_p()
+        d = None if param_dir is None else os.fsencode(param_dir)
+        rc = lib.po_init(int(device), d, C.byref(h))
+        if rc:
+            raise RuntimeError("po_init failed (%d): %s" % (rc, lib.po_last_error(None).decode()))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().po_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, load().po_last_error(self._h).decode()))
+
+    def set_conditions(self, mv=50.0, dv=0.0, dntp=0.8, dna_conc=50.0, temp_c=37.0, max_loop=30,
+                       max_nn_length=60):
+        self._check(load().po_set_conditions(self._h, mv, dv, dntp, dna_conc, temp_c, max_loop, max_nn_length),
+                    "po_set_conditions")
+
+    # ---- host-buffer calls ---------------------------------------------------
+    def tm_batch(self, oligos, with_gc=False):
+        oligos = np.ascontiguousarray(oligos, dtype=OLIGO_DTYPE)
+        n = len(oligos)
+        tm = np.empty(n, dtype=np.float64)
+        gc = np.empty(n, dtype=np.float64) if with_gc else None
+        self._check(load().po_tm_batch(self._h, oligos.ctypes.data, n, tm.ctypes.data,
+                                       gc.ctypes.data if with_gc else None), "po_tm_batch")
+        return (tm, gc) if with_gc else tm
+
+    def thal_batch(self, type_, a, b=None, out=None):
+        a = np.ascontiguousarray(a, dtype=OLIGO_DTYPE)
+        n = len(a)
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=OLIGO_DTYPE)
+            if len(b) != n:
+                raise ValueError("a and b differ in length")
+        if out is None:
+            out = np.empty(n, dtype=THAL_OUT_DTYPE)
+        self._check(load().po_thal_batch(self._h, type_, a.ctypes.data, b.ctypes.data if b is not None else None,
+                                         n, out.ctypes.data), "po_thal_batch")
+        return out
+
+    def oligo_props_batch(self, oligos, valid=None):
+        oligos = np.ascontiguousarray(oligos, dtype=OLIGO_DTYPE)
+        n = len(oligos)
+        out = np.empty(n, dtype=PROPS_DTYPE)
+        self._check(load().po_oligo_props_batch(self._h, oligos.ctypes.data, n,
+                                                C.byref(valid) if valid is not None else None,
+                                                out.ctypes.data), "po_oligo_props_batch")
+        return out
+
+    def count_relaxations(self, type_, a, b=None):
+        a = np.ascontiguousarray(a, dtype=OLIGO_DTYPE)
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=OLIGO_DTYPE)
+        v = C.c_int64()
+        self._check(load().po_thal_count_relaxations(self._h, type_, a.ctypes.data,
+                                                     b.ctypes.data if b is not None else None, len(a),
+                                                     C.byref(v)), "po_thal_count_relaxations")
+        return v.value
+
+    # ---- device-pointer calls (torch tensors / raw pointers) --------------------
+    def thal_batch_dev(self, type_, d_a, d_b, n, d_out, stream=None):
+        self._check(load().po_thal_batch_dev(self._h, type_, d_a, d_b, n, d_out, stream), "po_thal_batch_dev")
+
+    def tm_batch_dev(self, d_oligos, n, d_tm, d_gc=None, stream=None):
+        self._check(load().po_tm_batch_dev(self._h, d_oligos, n, d_tm, d_gc, stream), "po_tm_batch_dev")
+
+    def sync(self, stream=None):
+        self._check(load().po_sync(self._h, stream), "po_sync")
+
+    def launch_count(self):
+        return load().po_launch_count(self._h)
+
+    def measure_fp64_peak(self):
+        v = C.c_double()
+        self._check(load().po_measure_fp64_peak(self._h, C.byref(v)), "po_measure_fp64_peak")
+        return v.value

@@ -1,0 +1,50 @@
+"""Builds libpolyoligo_b200.so in-tree with nvcc for sm_100a.
+
+The library is plain CUDA C++ behind a C ABI (include/polyoligo_b200.h); it does
+not link against torch.  -fmad=false keeps every double operation individually
+rounded: the thal kernels promise results bit-identical to the scalar algorithm.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libpolyoligo_b200.so")
+SOURCES = ["po_lib.cu", "po_tables.cpp"]
+HEADERS = ["po_common.h", "po_thal.cuh", "po_thal_dimer.cuh", "po_thal_hairpin.cuh", "default_params.inc",
+           os.path.join("..", "..", "include", "polyoligo_b200.h")]
+
+
+def nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-fmad=false", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-shared", "-cudart", "static",
+           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(LIB)

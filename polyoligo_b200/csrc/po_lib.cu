@@ -1,0 +1,551 @@
+// po_lib.cu -- kernels, launchers and the C ABI of libpolyoligo_b200.so.
+// The ABI is declared in include/polyoligo_b200.h; each entry point names the
+// reference call it replaces there.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <string>
+
+#include "po_common.h"
+#include "po_thal.cuh"
+#include "po_thal_dimer.cuh"
+#include "po_thal_hairpin.cuh"
+
+// ============================================================================
+// kernels
+// ============================================================================
+
+__device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt) {
+    const uint4* src = reinterpret_cast<const uint4*>(gt);
+    uint4* dst = reinterpret_cast<uint4*>(tb);
+    for (int idx = threadIdx.x; idx < (int)(sizeof(SmemTables) / 16); idx += blockDim.x) dst[idx] = src[idx];
+    __syncthreads();
+}
+
+// Work distribution: every warp pulls the next item from a global counter, so
+// long pairs do not stall a fixed partition.  Items whose finite-cell count
+// exceeds CAP are appended to `overflow` and picked up by the large-CAP pass.
+//   list == nullptr : items are 0..n-1
+//   list != nullptr : items are list[0 .. *list_n)
+template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
+__global__ void __launch_bounds__(WARPS * 32)
+k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po_thal_out* __restrict__ out,
+       const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
+       const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
+       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    SmemTables* tb = reinterpret_cast<SmemTables*>(smem);
+    WarpWs<CAP>* wsAll = reinterpret_cast<WarpWs<CAP>*>(smem + sizeof(SmemTables));
+    stage_tables(tb, gt);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpWs<CAP>& ws = wsAll[warp];
+    const unsigned long long total = list ? *list_n : (unsigned long long)n;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(work, 1ull);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= total) break;
+        const long long item = list ? list[t] : (long long)t;
+        const uint4 oa = A[item];
+        // upper bound of the finite-cell count: exact count is cheap from base composition
+        if (HAIRPIN) {
+            int a, c, g, t_;
+            po_base_counts(oa, po_len(oa), a, c, g, t_);
+            const int ub = a * t_ + c * g;
+            if (ub > CAP) {
+                if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
+                continue;
+            }
+            thal_hairpin_warp<CAP, COUNT>(*tb, gt, ws, oa, K, out + item, relax);
+        } else {
+            const uint4 ob = B ? B[item] : oa;
+            int a1, c1, g1, t1, a2, c2, g2, t2;
+            po_base_counts(oa, po_len(oa), a1, c1, g1, t1);
+            po_base_counts(ob, po_len(ob), a2, c2, g2, t2);
+            const int ncell = a1 * t2 + c1 * g2 + g1 * c2 + t1 * a2;
+            if (ncell > CAP) {
+                if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
+                continue;
+            }
+            thal_dimer_warp<CAP, COUNT>(*tb, ws, oa, ob, K, out + item, relax);
+        }
+    }
+}
+
+// calcTm + GC content, one thread per oligo (upstream oligotm.c: seqtm/oligotm
+// with SantaLucia tables and SantaLucia salt correction).
+__constant__ int c_tm_dh[16] = {79, 84, 78, 72, 85, 80, 106, 78, 82, 98, 80, 84, 72, 82, 85, 79};
+__constant__ int c_tm_ds[16] = {222, 224, 210, 204, 227, 199, 272, 210, 222, 244, 199, 224, 213, 222, 227, 222};
+
+__device__ __forceinline__ double oligo_tm(const uint4& o, const PoConsts& K, double* gc_out) {
+    const int len = po_len(o);
+    int gc = 0;
+    for (int p = 0; p < len; ++p) {
+        const int b = po_base(o, p);
+        gc += (b == 1 || b == 2);
+    }
+    if (gc_out) *gc_out = len ? gc * 100.0 / len : 0.0;
+    if (po_bad(o) || len < 2) return -999999.9999;
+    if (len > K.max_nn_length)
+        return 81.5 + (16.6 * K.tm_log10_mv) + (41.0 * (((double)gc) / len)) - (600.0 / len);
+    int dh = 0, ds = 0;
+    bool sym = (len % 2 == 0);
+    for (int p = 0; p < len / 2 && sym; ++p) sym = (po_base(o, p) + po_base(o, len - 1 - p) == 3);
+    if (sym) ds += 14;
+    const int first = po_base(o, 0), last = po_base(o, len - 1);
+    if (first == 0 || first == 3) { ds += -41; dh += -23; } else { ds += 28; dh += -1; }
+    if (last == 0 || last == 3) { ds += -41; dh += -23; } else { ds += 28; dh += -1; }
+    int prev = first;
+    for (int p = 1; p < len; ++p) {
+        const int b = po_base(o, p);
+        dh += c_tm_dh[4 * prev + b];
+        ds += c_tm_ds[4 * prev + b];
+        prev = b;
+    }
+    const double delta_H = dh * -100.0;
+    double delta_S = ds * -0.1;
+    delta_S = delta_S + 0.368 * (len - 1) * K.tm_log_mv;
+    return delta_H / (delta_S + (sym ? K.tm_rlog_sym : K.tm_rlog_non)) - 273.15;
+}
+
+__global__ void k_tm(const uint4* __restrict__ A, long long n, double* __restrict__ tm, double* __restrict__ gc,
+                     const PoConsts K) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double g;
+    const double v = oligo_tm(A[t], K, &g);
+    tm[t] = v;
+    if (gc) gc[t] = g;
+}
+
+// Primer.calc_thermals + Primer.is_valid (reference lib_primer3.py:56-97) from
+// the three per-oligo evaluations.
+__global__ void k_props(const uint4* __restrict__ A, long long n, const po_thal_out* __restrict__ hp,
+                        const po_thal_out* __restrict__ hd, const PoConsts K, const po_valid_params V,
+                        int have_valid, po_oligo_props* __restrict__ out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint4 o = A[t];
+    po_oligo_props r;
+    double g;
+    r.tm = oligo_tm(o, K, &g);
+    r.gc_content = g;
+    r.hairpin_tm = hp[t].tm;
+    r.homodimer_tm = hd[t].tm;
+    r.length = po_len(o);
+    r.flags = (hp[t].flags | hd[t].flags) & PO_ITEM_SKIPPED;
+    if (have_valid && !(r.flags & PO_ITEM_SKIPPED)) {
+        bool ok = true;
+        if (r.length < V.min_size || r.length > V.max_size) ok = false;
+        if (r.gc_content < V.min_gc || r.gc_content > V.max_gc) ok = false;
+        if (r.tm < V.min_tm || r.tm > V.max_tm) ok = false;
+        if (r.hairpin_tm >= (r.tm - V.tm_delta)) ok = false;
+        if (r.homodimer_tm >= (r.tm - V.tm_delta)) ok = false;
+        if (ok) r.flags |= PO_PRIMER_VALID;
+    }
+    out[t] = r;
+}
+
+// register-resident FP64 FMA chains: the compute-roofline denominator
+__global__ void k_fp64_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-7;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ============================================================================
+// context
+// ============================================================================
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct po_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    PoTables* d_tables = nullptr;
+    PoConsts K;
+    int num_sms = 0;
+    std::string err;
+    int64_t launches = 0;
+    // grow-only device scratch
+    DevBuf a, b, out, out2, tmv, gcv, props, overflow;
+    unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
+    // pinned staging for the host entry points
+    DevBuf h_in, h_out;
+    int fast_cap = 0;  // 0 = choose by environment / default
+};
+
+static std::string g_init_error;
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            return PO_E_CUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+static int ensure(po_ctx* ctx, DevBuf& buf, size_t bytes) {
+    if (bytes <= buf.cap) return PO_OK;
+    if (buf.p) CK(cudaFree(buf.p));
+    buf.p = nullptr;
+    buf.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&buf.p, want));
+    buf.cap = want;
+    return PO_OK;
+}
+
+static void resolve_conditions(PoConsts* K, double mv, double dv, double dntp, double dna, double temp_c,
+                               int max_loop, int max_nn) {
+    // thal saltCorrectS(): if (dv <= 0) dntp = dv
+    double d = dntp;
+    if (dv <= 0) d = dv;
+    K->salt_corr = 0.368 * ((log((mv + 120 * (sqrt(fmax(0.0, dv - d)))) / 1000)));
+    K->rc_sym = 1.9872 * log(dna / 1000000000.0);
+    K->rc_nonsym = 1.9872 * log(dna / 4000000000.0);
+    K->temp_k = temp_c + 273.15;
+    // oligotm divalent_to_monovalent()
+    double dv2 = dv, dn2 = dntp;
+    if (dv2 == 0) dn2 = 0;
+    if (dv2 < dn2) dv2 = dn2;
+    const double mv_eff = mv + 120 * (sqrt(dv2 - dn2));
+    K->tm_log_mv = log(mv_eff / 1000.0);
+    K->tm_log10_mv = log10(mv_eff / 1000.0);
+    K->tm_rlog_sym = 1.987 * log(dna / 1000000000.0);
+    K->tm_rlog_non = 1.987 * log(dna / 4000000000.0);
+    K->max_loop = max_loop;
+    K->max_nn_length = max_nn;
+}
+
+extern "C" int po_init(int device, const char* param_dir, po_ctx** out) {
+    if (!out) return PO_E_INVALID;
+    *out = nullptr;
+    PoTables host;
+    std::string err;
+    if (!po_load_tables(param_dir, &host, &err)) {
+        g_init_error = err;
+        return PO_E_PARAMS;
+    }
+    po_ctx* ctx = new po_ctx();
+    ctx->device = device;
+    auto fail = [&](const char* what, cudaError_t e) {
+        g_init_error = std::string(what) + ": " + cudaGetErrorString(e);
+        delete ctx;
+        return PO_E_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+    ctx->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return fail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&ctx->d_tables, sizeof(PoTables))) != cudaSuccess) return fail("cudaMalloc tables", e);
+    if ((e = cudaMemcpy(ctx->d_tables, &host, sizeof(PoTables), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail("cudaMemcpy tables", e);
+    if ((e = cudaMalloc(&ctx->d_ctr, 8 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc ctr", e);
+    resolve_conditions(&ctx->K, 50.0, 0.0, 0.8, 50.0, 37.0, 30, 60);
+    const char* fc = getenv("PO_FAST_CAP");
+    if (fc) ctx->fast_cap = atoi(fc);
+    *out = ctx;
+    return PO_OK;
+}
+
+extern "C" void po_destroy(po_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    DevBuf* bufs[] = {&ctx->a, &ctx->b, &ctx->out, &ctx->out2, &ctx->tmv, &ctx->gcv, &ctx->props, &ctx->overflow};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
+    if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* po_last_error(const po_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+extern "C" int po_set_conditions(po_ctx* ctx, double mv, double dv, double dntp, double dna_nM, double temp_c,
+                                 int max_loop, int max_nn_length) {
+    if (!ctx) return PO_E_INVALID;
+    if (mv < 0 || dv < 0 || dntp < 0 || dna_nM <= 0 || max_loop < 0 || max_loop > 30) {
+        ctx->err = "po_set_conditions: argument out of range (max_loop must be 0..30)";
+        return PO_E_INVALID;
+    }
+    resolve_conditions(&ctx->K, mv, dv, dntp, dna_nM, temp_c, max_loop, max_nn_length);
+    return PO_OK;
+}
+
+extern "C" int64_t po_launch_count(const po_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ============================================================================
+// packing (host)
+// ============================================================================
+extern "C" int po_pack(const char* ascii, const int64_t* offsets, int64_t n, po_oligo* packed) {
+    if (!ascii || !offsets || !packed || n < 0) return PO_E_INVALID;
+    for (int64_t k = 0; k < n; ++k) {
+        const int64_t len = offsets[k + 1] - offsets[k];
+        const char* s = ascii + offsets[k];
+        uint32_t w[4] = {0, 0, 0, 0};
+        uint32_t meta = 0;
+        const int64_t m = len > PO_MAX_OLIGO_LEN ? PO_MAX_OLIGO_LEN : len;
+        for (int64_t p = 0; p < m; ++p) {
+            uint32_t code = 0;
+            switch (s[p]) {
+                case 'A': case 'a': code = 0; break;
+                case 'C': case 'c': code = 1; break;
+                case 'G': case 'g': code = 2; break;
+                case 'T': case 't': code = 3; break;
+                case 'N': case 'n': case 'R': case 'r': case 'Y': case 'y': case 'S': case 's':
+                case 'W': case 'w': case 'K': case 'k': case 'M': case 'm': case 'B': case 'b':
+                case 'D': case 'd': case 'H': case 'h': case 'V': case 'v': case 'U': case 'u':
+                    meta |= PO_OLIGO_HAS_N; break;
+                default: meta |= PO_OLIGO_BAD_CHAR; break;
+            }
+            w[p >> 4] |= code << (2 * (p & 15));
+        }
+        if (len > PO_MAX_OLIGO_LEN) meta |= PO_OLIGO_BAD_CHAR;  // too long for a record: never evaluated
+        meta |= (uint32_t)m;
+        w[3] |= meta << 24;
+        packed[k].w[0] = w[0];
+        packed[k].w[1] = w[1];
+        packed[k].w[2] = w[2];
+        packed[k].w[3] = w[3];
+    }
+    return PO_OK;
+}
+
+extern "C" int po_unpack(const po_oligo* packed, int64_t n, char* out) {
+    if (!packed || !out || n < 0) return PO_E_INVALID;
+    static const char L[4] = {'A', 'C', 'G', 'T'};
+    for (int64_t k = 0; k < n; ++k) {
+        const uint32_t* w = packed[k].w;
+        const int len = (w[3] >> 24) & PO_OLIGO_LEN_MASK;
+        char* o = out + 61 * k;
+        for (int p = 0; p < len; ++p) o[p] = L[(w[p >> 4] >> (2 * (p & 15))) & 3];
+        o[len] = 0;
+    }
+    return PO_OK;
+}
+
+// ============================================================================
+// launchers
+// ============================================================================
+template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
+static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4* B, long long n, po_thal_out* out,
+                       unsigned long long* work, const long long* list, const unsigned long long* list_n,
+                       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax) {
+    const size_t smem = sizeof(SmemTables) + WARPS * sizeof(WarpWs<CAP>);
+    auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
+    if (per_sm < 1) {
+        ctx->err = "thal kernel does not fit on an SM";
+        return PO_E_CUDA;
+    }
+    long long blocks = (long long)ctx->num_sms * per_sm;
+    if (!list) {
+        const long long need = (n + WARPS - 1) / WARPS;
+        if (need < blocks) blocks = need;
+    }
+    if (blocks < 1) blocks = 1;
+    kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, B, n, out, ctx->d_tables, ctx->K, work, list, list_n, overflow,
+                                                     overflow_n, relax);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PO_OK;
+}
+
+// two passes: a small-CAP pass with high occupancy, then a full-capacity pass
+// over whatever overflowed (repetitive / low-complexity inputs)
+template <bool COUNT>
+static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out, cudaStream_t st) {
+    if (n == 0) return PO_OK;
+    int rc = ensure(ctx, ctx->overflow, sizeof(long long) * (size_t)n);
+    if (rc) return rc;
+    unsigned long long* ctr = ctx->d_ctr;
+    CK(cudaMemsetAsync(ctr, 0, 5 * sizeof(unsigned long long), st));
+    const uint4* A = (const uint4*)d_a;
+    const uint4* B = (const uint4*)d_b;
+    po_thal_out* out = (po_thal_out*)d_out;
+    long long* ovf = (long long*)ctx->overflow.p;
+    const int cap = ctx->fast_cap ? ctx->fast_cap : 512;
+    if (type == PO_THAL_HAIRPIN) {
+        if (cap <= 256) rc = launch_thal<256, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+        else if (cap <= 512) rc = launch_thal<512, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+        else rc = launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+        if (rc) return rc;
+        return launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 2, ovf, ctr + 1, ovf, ctr + 4, ctr + 7);
+    }
+    if (type != PO_THAL_ANY) {
+        ctx->err = "po_thal: only PO_THAL_ANY and PO_THAL_HAIRPIN are implemented on the device";
+        return PO_E_INVALID;
+    }
+    if (cap <= 256) rc = launch_thal<256, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+    else if (cap <= 512) rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+    else rc = launch_thal<1024, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+    if (rc) return rc;
+    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, ovf, ctr + 1, ovf, ctr + 4, ctr + 7);
+}
+
+extern "C" int po_thal_batch_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out,
+                                 void* stream) {
+    if (!ctx || !d_a || !d_out || n < 0) return PO_E_INVALID;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    return thal_dev<false>(ctx, type, d_a, d_b, n, d_out, st);
+}
+
+extern "C" int po_tm_batch_dev(po_ctx* ctx, const void* d_oligos, int64_t n, void* d_tm, void* d_gc, void* stream) {
+    if (!ctx || !d_oligos || !d_tm || n < 0) return PO_E_INVALID;
+    if (n == 0) return PO_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    const int threads = 256;
+    const long long blocks = (n + threads - 1) / threads;
+    k_tm<<<(unsigned)blocks, threads, 0, st>>>((const uint4*)d_oligos, n, (double*)d_tm, (double*)d_gc, ctx->K);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return PO_OK;
+}
+
+extern "C" int po_sync(po_ctx* ctx, void* stream) {
+    if (!ctx) return PO_E_INVALID;
+    CK(cudaStreamSynchronize(stream ? (cudaStream_t)stream : ctx->stream));
+    return PO_OK;
+}
+
+// ---- host-buffer entry points -------------------------------------------------
+static int pinned(po_ctx* ctx, DevBuf& buf, size_t bytes) {
+    if (bytes <= buf.cap) return PO_OK;
+    if (buf.p) CK(cudaFreeHost(buf.p));
+    buf.p = nullptr;
+    buf.cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMallocHost(&buf.p, want));
+    buf.cap = want;
+    return PO_OK;
+}
+
+extern "C" int po_tm_batch(po_ctx* ctx, const po_oligo* oligos, int64_t n, double* tm, double* gc) {
+    if (!ctx || !oligos || !tm || n < 0) return PO_E_INVALID;
+    if (n == 0) return PO_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->tmv, sizeof(double) * (size_t)n))) return rc;
+    if (gc && (rc = ensure(ctx, ctx->gcv, sizeof(double) * (size_t)n))) return rc;
+    CK(cudaMemcpyAsync(ctx->a.p, oligos, sizeof(po_oligo) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = po_tm_batch_dev(ctx, ctx->a.p, n, ctx->tmv.p, gc ? ctx->gcv.p : nullptr, ctx->stream))) return rc;
+    CK(cudaMemcpyAsync(tm, ctx->tmv.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (gc) CK(cudaMemcpyAsync(gc, ctx->gcv.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PO_OK;
+}
+
+extern "C" int po_thal_batch(po_ctx* ctx, int type, const po_oligo* a, const po_oligo* b, int64_t n,
+                             po_thal_out* out) {
+    if (!ctx || !a || !out || n < 0) return PO_E_INVALID;
+    if (n == 0) return PO_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * (size_t)n))) return rc;
+    if (b && (rc = ensure(ctx, ctx->b, sizeof(po_oligo) * (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->out, sizeof(po_thal_out) * (size_t)n))) return rc;
+    CK(cudaMemcpyAsync(ctx->a.p, a, sizeof(po_oligo) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(ctx->b.p, b, sizeof(po_oligo) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = thal_dev<false>(ctx, type, ctx->a.p, b ? ctx->b.p : nullptr, n, ctx->out.p, ctx->stream))) return rc;
+    CK(cudaMemcpyAsync(out, ctx->out.p, sizeof(po_thal_out) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PO_OK;
+}
+
+extern "C" int po_thal_count_relaxations(po_ctx* ctx, int type, const po_oligo* a, const po_oligo* b, int64_t n,
+                                         int64_t* relaxations) {
+    if (!ctx || !a || !relaxations || n < 0) return PO_E_INVALID;
+    *relaxations = 0;
+    if (n == 0) return PO_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * (size_t)n))) return rc;
+    if (b && (rc = ensure(ctx, ctx->b, sizeof(po_oligo) * (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->out, sizeof(po_thal_out) * (size_t)n))) return rc;
+    CK(cudaMemcpyAsync(ctx->a.p, a, sizeof(po_oligo) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) CK(cudaMemcpyAsync(ctx->b.p, b, sizeof(po_oligo) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctr + 7, 0, sizeof(unsigned long long), ctx->stream));
+    if ((rc = thal_dev<true>(ctx, type, ctx->a.p, b ? ctx->b.p : nullptr, n, ctx->out.p, ctx->stream))) return rc;
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, ctx->d_ctr + 7, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *relaxations = (int64_t)v;
+    return PO_OK;
+}
+
+extern "C" int po_oligo_props_batch(po_ctx* ctx, const po_oligo* oligos, int64_t n, const po_valid_params* valid,
+                                    po_oligo_props* out) {
+    if (!ctx || !oligos || !out || n < 0) return PO_E_INVALID;
+    if (n == 0) return PO_OK;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->out, sizeof(po_thal_out) * (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->out2, sizeof(po_thal_out) * (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->props, sizeof(po_oligo_props) * (size_t)n))) return rc;
+    CK(cudaMemcpyAsync(ctx->a.p, oligos, sizeof(po_oligo) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = thal_dev<false>(ctx, PO_THAL_HAIRPIN, ctx->a.p, nullptr, n, ctx->out.p, ctx->stream))) return rc;
+    if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, ctx->a.p, nullptr, n, ctx->out2.p, ctx->stream))) return rc;
+    po_valid_params V;
+    memset(&V, 0, sizeof V);
+    if (valid) V = *valid;
+    const int threads = 256;
+    const long long blocks = (n + threads - 1) / threads;
+    k_props<<<(unsigned)blocks, threads, 0, ctx->stream>>>((const uint4*)ctx->a.p, n, (const po_thal_out*)ctx->out.p,
+                                                          (const po_thal_out*)ctx->out2.p, ctx->K, V, valid ? 1 : 0,
+                                                          (po_oligo_props*)ctx->props.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->props.p, sizeof(po_oligo_props) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PO_OK;
+}
+
+extern "C" int po_measure_fp64_peak(po_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return PO_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int threads = 256, blocks = ctx->num_sms * 8, iters = 1 << 16;
+    int rc;
+    if ((rc = ensure(ctx, ctx->tmv, sizeof(double) * (size_t)threads * blocks))) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0, ctx->stream));
+        k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->tmv.p, iters);
+        ctx->launches++;
+        CK(cudaEventRecord(e1, ctx->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return PO_OK;
+}
