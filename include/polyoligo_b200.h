@@ -130,6 +130,15 @@ int po_thal_batch(po_ctx *ctx, int type, const po_oligo *a, const po_oligo *b, i
 int po_oligo_props_batch(po_ctx *ctx, const po_oligo *oligos, int64_t n,
                          const po_valid_params *valid, po_oligo_props *out);
 
+/* Score-only path for n given primer pairs (the shape of reverse_engineer.py:
+ * process_assay, reference reverse_engineer.py:61-112, and of BASELINE config 4):
+ * calcHeterodimer(a,b) + calcHairpin(a) + calcHairpin(b) + calcTm(a) + calcTm(b).
+ * Any output pointer may be NULL to skip that evaluation.  Large batches are
+ * processed in bounded device-memory chunks. */
+int po_score_pairs_batch(po_ctx *ctx, const po_oligo *a, const po_oligo *b, int64_t n,
+                         po_thal_out *het, po_thal_out *hairpin_a, po_thal_out *hairpin_b,
+                         double *tm_a, double *tm_b);
+
 /* ---- scoring, DEVICE buffers (no copies; asynchronous on `stream`) -------- */
 /* Pointers are CUDA device pointers; stream is a cudaStream_t (NULL = the
  * context's own stream).  The call returns after enqueueing. */
@@ -137,6 +146,9 @@ int po_tm_batch_dev(po_ctx *ctx, const void *d_oligos, int64_t n, void *d_tm, vo
                     void *stream);
 int po_thal_batch_dev(po_ctx *ctx, int type, const void *d_a, const void *d_b, int64_t n,
                       void *d_out, void *stream);
+int po_score_pairs_batch_dev(po_ctx *ctx, const void *d_a, const void *d_b, int64_t n,
+                             void *d_het, void *d_hairpin_a, void *d_hairpin_b, void *d_tm_a,
+                             void *d_tm_b, void *stream);
 /* Blocks until everything enqueued on `stream` (NULL = context stream) is done. */
 int po_sync(po_ctx *ctx, void *stream);
 

@@ -46,6 +46,10 @@ EXPORTS = {
     "po_tm_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "po_thal_batch_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_void_p]),
+    "po_score_pairs_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "po_score_pairs_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "po_launch_count": (C.c_int64, [C.c_void_p]),
     "po_thal_count_relaxations": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
@@ -167,6 +171,30 @@ class Context:
                                                 C.byref(valid) if valid is not None else None,
                                                 out.ctypes.data), "po_oligo_props_batch")
         return out
+
+    def score_pairs(self, a, b, out=None):
+        """Heterodimer(a,b) + hairpin(a) + hairpin(b) + Tm(a) + Tm(b) for host arrays.
+
+        ``out`` may carry preallocated (e.g. pinned) arrays under the keys
+        het / hairpin_a / hairpin_b / tm_a / tm_b."""
+        a = np.ascontiguousarray(a, dtype=OLIGO_DTYPE)
+        b = np.ascontiguousarray(b, dtype=OLIGO_DTYPE)
+        n = len(a)
+        if len(b) != n:
+            raise ValueError("a and b differ in length")
+        if out is None:
+            out = {"het": np.empty(n, dtype=THAL_OUT_DTYPE), "hairpin_a": np.empty(n, dtype=THAL_OUT_DTYPE),
+                   "hairpin_b": np.empty(n, dtype=THAL_OUT_DTYPE), "tm_a": np.empty(n, dtype=np.float64),
+                   "tm_b": np.empty(n, dtype=np.float64)}
+        self._check(load().po_score_pairs_batch(self._h, a.ctypes.data, b.ctypes.data, n,
+                                                out["het"].ctypes.data, out["hairpin_a"].ctypes.data,
+                                                out["hairpin_b"].ctypes.data, out["tm_a"].ctypes.data,
+                                                out["tm_b"].ctypes.data), "po_score_pairs_batch")
+        return out
+
+    def score_pairs_dev(self, d_a, d_b, n, d_het, d_hp_a, d_hp_b, d_tm_a, d_tm_b, stream=None):
+        self._check(load().po_score_pairs_batch_dev(self._h, d_a, d_b, n, d_het, d_hp_a, d_hp_b, d_tm_a, d_tm_b,
+                                                    stream), "po_score_pairs_batch_dev")
 
     def count_relaxations(self, type_, a, b=None):
         a = np.ascontiguousarray(a, dtype=OLIGO_DTYPE)

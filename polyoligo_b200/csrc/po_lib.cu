@@ -178,7 +178,7 @@ struct po_ctx {
     std::string err;
     int64_t launches = 0;
     // grow-only device scratch
-    DevBuf a, b, out, out2, tmv, gcv, props, overflow;
+    DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow;
     unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
     // pinned staging for the host entry points
     DevBuf h_in, h_out;
@@ -266,7 +266,7 @@ extern "C" int po_init(int device, const char* param_dir, po_ctx** out) {
 extern "C" void po_destroy(po_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->a, &ctx->b, &ctx->out, &ctx->out2, &ctx->tmv, &ctx->gcv, &ctx->props, &ctx->overflow};
+    DevBuf* bufs[] = {&ctx->a, &ctx->b, &ctx->out, &ctx->out2, &ctx->out3, &ctx->tmv, &ctx->gcv, &ctx->props, &ctx->overflow};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
@@ -470,6 +470,54 @@ extern "C" int po_thal_batch(po_ctx* ctx, int type, const po_oligo* a, const po_
     if ((rc = thal_dev<false>(ctx, type, ctx->a.p, b ? ctx->b.p : nullptr, n, ctx->out.p, ctx->stream))) return rc;
     CK(cudaMemcpyAsync(out, ctx->out.p, sizeof(po_thal_out) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return PO_OK;
+}
+
+extern "C" int po_score_pairs_batch_dev(po_ctx* ctx, const void* d_a, const void* d_b, int64_t n, void* d_het,
+                                        void* d_hairpin_a, void* d_hairpin_b, void* d_tm_a, void* d_tm_b,
+                                        void* stream) {
+    if (!ctx || !d_a || !d_b || n < 0) return PO_E_INVALID;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc;
+    if (d_het && (rc = thal_dev<false>(ctx, PO_THAL_ANY, d_a, d_b, n, d_het, st))) return rc;
+    if (d_hairpin_a && (rc = thal_dev<false>(ctx, PO_THAL_HAIRPIN, d_a, nullptr, n, d_hairpin_a, st))) return rc;
+    if (d_hairpin_b && (rc = thal_dev<false>(ctx, PO_THAL_HAIRPIN, d_b, nullptr, n, d_hairpin_b, st))) return rc;
+    if (d_tm_a && (rc = po_tm_batch_dev(ctx, d_a, n, d_tm_a, nullptr, st))) return rc;
+    if (d_tm_b && (rc = po_tm_batch_dev(ctx, d_b, n, d_tm_b, nullptr, st))) return rc;
+    return PO_OK;
+}
+
+extern "C" int po_score_pairs_batch(po_ctx* ctx, const po_oligo* a, const po_oligo* b, int64_t n, po_thal_out* het,
+                                    po_thal_out* hairpin_a, po_thal_out* hairpin_b, double* tm_a, double* tm_b) {
+    if (!ctx || !a || !b || n < 0) return PO_E_INVALID;
+    if (n == 0) return PO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t chunk = 1 << 22;  // bounds device scratch to ~0.7 GB
+    const int64_t m0 = n < chunk ? n : chunk;
+    int rc;
+    if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * (size_t)m0))) return rc;
+    if ((rc = ensure(ctx, ctx->b, sizeof(po_oligo) * (size_t)m0))) return rc;
+    if (het && (rc = ensure(ctx, ctx->out, sizeof(po_thal_out) * (size_t)m0))) return rc;
+    if (hairpin_a && (rc = ensure(ctx, ctx->out2, sizeof(po_thal_out) * (size_t)m0))) return rc;
+    if (hairpin_b && (rc = ensure(ctx, ctx->out3, sizeof(po_thal_out) * (size_t)m0))) return rc;
+    if (tm_a && (rc = ensure(ctx, ctx->tmv, sizeof(double) * (size_t)m0))) return rc;
+    if (tm_b && (rc = ensure(ctx, ctx->gcv, sizeof(double) * (size_t)m0))) return rc;
+    cudaStream_t st = ctx->stream;
+    for (int64_t s = 0; s < n; s += chunk) {
+        const int64_t m = (n - s) < chunk ? (n - s) : chunk;
+        CK(cudaMemcpyAsync(ctx->a.p, a + s, sizeof(po_oligo) * (size_t)m, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->b.p, b + s, sizeof(po_oligo) * (size_t)m, cudaMemcpyHostToDevice, st));
+        if ((rc = po_score_pairs_batch_dev(ctx, ctx->a.p, ctx->b.p, m, het ? ctx->out.p : nullptr,
+                                           hairpin_a ? ctx->out2.p : nullptr, hairpin_b ? ctx->out3.p : nullptr,
+                                           tm_a ? ctx->tmv.p : nullptr, tm_b ? ctx->gcv.p : nullptr, st)))
+            return rc;
+        if (het) CK(cudaMemcpyAsync(het + s, ctx->out.p, sizeof(po_thal_out) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        if (hairpin_a) CK(cudaMemcpyAsync(hairpin_a + s, ctx->out2.p, sizeof(po_thal_out) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        if (hairpin_b) CK(cudaMemcpyAsync(hairpin_b + s, ctx->out3.p, sizeof(po_thal_out) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        if (tm_a) CK(cudaMemcpyAsync(tm_a + s, ctx->tmv.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        if (tm_b) CK(cudaMemcpyAsync(tm_b + s, ctx->gcv.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return PO_OK;
 }
 

@@ -1,0 +1,252 @@
+#!/usr/bin/env python3
+"""Generates the golden fixtures under tests/golden/ by running the REFERENCE's
+own Python (/root/reference/src/polyoligo, imported here in the build
+container) on seeded synthetic inputs.
+
+The reference's thermodynamics come from primer3-py, which cannot be installed
+offline, so ``primer3.thermoanalysis.ThermoAnalysis`` is backed by the CPU
+oracle (tests/golden/ref_stubs.py).  Everything ABOVE that call -- candidate
+enumeration, validity filter, heterodimer predicates, masks, scoring, classify
+and prune -- is the reference's unmodified code, so these fixtures pin the
+host-logic rows of SURVEY.md 8a (a2, a3, a4, a8, a9) to the reference itself.
+
+Run (only where /root/reference exists):  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from oracle.oracle import Oracle  # noqa: E402
+import ref_stubs  # noqa: E402
+
+ref_stubs.install(Oracle())
+import polyoligo.lib_primer3 as lp  # noqa: E402
+import polyoligo._lib_kasp as lk  # noqa: E402
+import polyoligo.scoring as sc  # noqa: E402
+import polyoligo.lib_utils as lu  # noqa: E402
+
+KASP_GLOBALS = dict(PRIMER_MIN_SIZE=18, PRIMER_MAX_SIZE=25, PRIMER_MIN_GC=20.0, PRIMER_MAX_GC=80.0,
+                    PRIMER_MIN_TM=55.0, PRIMER_MAX_TM=65.0)   # reference data/PRIMER3_KASP.yaml
+VIC = "GAAGGTCGGAGTCAACGGATT"   # reference cli_kasp.py:65
+FAM = "GAAGGTGACCAAGTTCATGCT"   # reference cli_kasp.py:72
+
+
+def rand_seq(rng, n, gc=0.5):
+    p = [(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2]
+    return "".join(np.array(list("ACGT"))[rng.choice(4, n, p=p)])
+
+
+def dump(name, obj):
+    with open(os.path.join(HERE, name), "w") as f:
+        json.dump(obj, f, indent=0, sort_keys=True)
+    print("wrote", name)
+
+
+def make_hroi(seq, start, pos1, ref, alt):
+    marker = types.SimpleNamespace(pos1=pos1, ref=ref, alt=alt)
+    return types.SimpleNamespace(seq=seq, start=start, stop=start + len(seq) - 1, marker=marker,
+                                 chrom="chrT", name="m")
+
+
+def golden_marker_primers(rng):
+    """a3: get_marker_primers (reference _lib_kasp.py:295-359), with and without the validity filter."""
+    lp.set_tm_delta(5.0)
+    lp.PRIMER3_GLOBALS.clear()
+    lp.PRIMER3_GLOBALS.update(KASP_GLOBALS)
+    cases = []
+    specs = [("snp", 1, 1)] * 14 + [("del", 3, 1), ("del", 5, 2), ("ins", 1, 4), ("ins", 2, 6), ("mnp", 2, 2),
+                                    ("mnp", 3, 3)]
+    for kind, rl, al in specs:
+        seq = rand_seq(rng, 500, gc=rng.choice([0.42, 0.5, 0.58]))
+        start = int(rng.integers(1000, 100000))
+        idx = 249
+        ref = seq[idx:idx + rl]
+        alt = ref
+        while alt == ref or (al == rl == 1 and alt == ref):
+            alt = rand_seq(rng, al)
+        hroi = make_hroi(seq, start, start + idx, ref, alt)
+        real_valid = lp.Primer.is_valid
+        lp.Primer.is_valid = lambda self: True          # every enumerated candidate, in order
+        allc = lk.get_marker_primers(hroi)
+        lp.Primer.is_valid = real_valid
+        kept = lk.get_marker_primers(hroi)
+        cases.append({
+            "seq": seq, "start": start, "stop": hroi.stop, "pos1": hroi.marker.pos1, "ref": ref, "alt": alt,
+            "all": [{"dir": pp.dir, "ref": pp.primers[pp.dir].sequence, "alt": pp.primers["A"].sequence}
+                    for pp in allc],
+            "kept": [{"dir": pp.dir, "ref": pp.primers[pp.dir].sequence, "alt": pp.primers["A"].sequence,
+                      "tm_ref": pp.primers[pp.dir].tm, "tm_alt": pp.primers["A"].tm} for pp in kept]})
+    dump("kasp_marker_primers.json", {"globals": KASP_GLOBALS, "tm_delta": 5.0, "cases": cases})
+
+
+def golden_is_valid(rng):
+    """a1/a2: Primer.calc_thermals / is_valid (reference lib_primer3.py:56-97)."""
+    lp.PRIMER3_GLOBALS.clear()
+    lp.PRIMER3_GLOBALS.update(KASP_GLOBALS)
+    rows = []
+    for tm_delta in (5.0, 10.0):
+        lp.set_tm_delta(tm_delta)
+        for _ in range(150):
+            s = rand_seq(rng, int(rng.integers(16, 28)), gc=rng.choice([0.3, 0.5, 0.7]))
+            if rng.random() < 0.05:
+                k = int(rng.integers(0, len(s)))
+                s = s[:k] + "N" + s[k + 1:]
+            p = lp.Primer(sequence=s)
+            ok = p.is_valid()
+            rows.append({"seq": s, "tm_delta": tm_delta, "valid": bool(ok), "tm": p.tm, "hairpin_tm": p.hairpin_tm,
+                         "homodimer_tm": p.homodimer_tm, "gc": p.gc_content, "nN": p.nN, "length": p.length})
+    lp.set_tm_delta(5.0)
+    dump("is_valid.json", {"globals": KASP_GLOBALS, "rows": rows})
+
+
+def golden_heterodimer(rng):
+    """a8: PrimerPair.check_heterodimerization, PCR (lib_primer3.py:147-164) and KASP (_lib_kasp.py:89-117)."""
+    lp.PRIMER3_GLOBALS.clear()
+    lp.PRIMER3_GLOBALS.update(KASP_GLOBALS)
+    pcr, kasp = [], []
+    for tm_delta in (5.0, 2.0):
+        lp.set_tm_delta(tm_delta)
+        for k in range(60):
+            f = rand_seq(rng, int(rng.integers(18, 26)))
+            r = rand_seq(rng, int(rng.integers(18, 26)))
+            if k % 7 == 0:   # force a strong dimer
+                r = lp.Seq(f[-12:]).reverse_complement() + r[12:]
+            pp = lp.PrimerPair()
+            pp.tm_delta = tm_delta
+            pp.primers["F"].sequence = f
+            pp.primers["R"].sequence = str(r)
+            for d in "FR":
+                pp.primers[d].tm_delta = tm_delta
+            pp.check_heterodimerization()
+            pcr.append({"F": f, "R": str(r), "tm_delta": tm_delta, "dimer": bool(pp.dimer),
+                        "tm_F": pp.primers["F"].tm, "tm_R": pp.primers["R"].tm})
+        for k in range(60):
+            direction = "F" if k % 2 == 0 else "R"
+            core = rand_seq(rng, int(rng.integers(18, 26)))
+            alt = core[:-1] + rng.choice([c for c in "ACGT" if c != core[-1]])
+            com = rand_seq(rng, int(rng.integers(18, 26)))
+            if k % 5 == 0:
+                com = str(lp.Seq((VIC + core)[-14:]).reverse_complement()) + com[14:]
+            pp = lk.PrimerPair()
+            pp.tm_delta = tm_delta
+            pp.dir = direction
+            pp.primers[direction].sequence = core
+            pp.primers["A"].sequence = alt
+            pp.primers["R" if direction == "F" else "F"].sequence = com
+            pp.add_reporter_dyes([VIC, FAM])
+            pp.check_heterodimerization()
+            kasp.append({"dir": direction, "F": pp.primers["F"].sequence, "R": pp.primers["R"].sequence,
+                         "A": pp.primers["A"].sequence, "tm_delta": tm_delta, "reporters": [VIC, FAM],
+                         "ref_dimer": bool(pp.ref_dimer), "alt_dimer": bool(pp.alt_dimer)})
+    lp.set_tm_delta(5.0)
+    dump("heterodimer_checks.json", {"pcr": pcr, "kasp": kasp})
+
+
+def golden_scoring(rng):
+    """a9: scoring.score_* (scoring.py:4-151), PCR.classify / prune (lib_primer3.py:425-463, _lib_kasp.py:278-291)."""
+    rows = []
+    pools = {"KASP": [], "PCR": [], "HRM": []}
+    for k in range(240):
+        assay = ["KASP", "PCR", "HRM", "CAPS"][k % 4]
+        keys = ["F", "R", "A"] if assay == "KASP" else ["F", "R"]
+        pp = types.SimpleNamespace()
+        base = rng.uniform(55, 65)
+        spread = rng.choice([0.5, 1.5, 3.0, 6.0])
+        pp.primers = {d: types.SimpleNamespace(tm=float(base + rng.uniform(-spread, spread)),
+                                               max_aaf=float(rng.choice([0.0, 0.0, 0.05, 0.099, 0.1, 0.3])))
+                      for d in keys}
+        pp.offtargets = ["x"] * int(rng.choice([0, 0, 1, 3]))
+        pp.dimer = bool(rng.random() < 0.3)
+        pp.ref_dimer = bool(rng.random() < 0.2)
+        pp.alt_dimer = bool(rng.random() < 0.2)
+        pp.max_indel_size = int(rng.choice([0, 0, 1, 49, 50, 120]))
+        pp.hrm = {"delta": float(rng.choice([0.0, 0.3, 0.5, 0.7, 1.0, 1.8]))}
+        goodness, qcode = sc.get_score_fnc(assay)(pp)
+        row = {"assay": assay, "tms": [pp.primers[d].tm for d in keys],
+               "max_aafs": [pp.primers[d].max_aaf for d in keys], "n_offtargets": len(pp.offtargets),
+               "dimer": pp.dimer, "ref_dimer": pp.ref_dimer, "alt_dimer": pp.alt_dimer,
+               "max_indel_size": pp.max_indel_size, "hrm_delta": pp.hrm["delta"],
+               "goodness": int(goodness), "qcode": qcode}
+        rows.append(row)
+        if assay in pools:
+            pp.goodness, pp.qcode, pp.uid = goodness, qcode, len(pools[assay])
+            pp.score = lambda assay_name, pp=pp: None       # already scored
+            pools[assay].append(pp)
+    prune = {}
+    for assay, pps in pools.items():
+        for n in (3, 10, 1000):
+            pcr = lk.PCR() if assay == "KASP" else lp.PCR()
+            pcr.pps = pps
+            pcr.classify(assay)
+            if assay == "KASP":
+                pcr.prune(n)
+            else:
+                pcr.prune(n, assay_name=assay)
+            order = []
+            for score in sorted(pcr.pps_pruned.keys(), reverse=True):   # report order (_lib_kasp.py:369)
+                order += [pp.uid for pp in pcr.pps_pruned[score]]
+            prune["%s/%d" % (assay, n)] = {
+                "goodness": [int(pp.goodness) for pp in pps], "hrm_delta": [pp.hrm["delta"] for pp in pps],
+                "order": order}
+    dump("scoring.json", {"rows": rows, "prune": prune})
+
+
+def golden_masks(rng):
+    """a4: include_mut_in_included_maps, the KASP marker-window step, excluded regions,
+    list_2_ranges, reduce_ivs (lib_primer3.py:564-600, _lib_kasp.py:681-684, lib_utils.py:144-261)."""
+    cases = []
+    for k in range(12):
+        n = 500
+        start = [int(rng.integers(1000, 10 ** 6)), 20, 3, 26][k % 4] if k >= 8 else int(rng.integers(1000, 10 ** 6))
+        mism = rng.random(n) < 0.05
+        partial = mism | (rng.random(n) < 0.15)
+        allm = np.ones(n, dtype=bool)
+        if k % 3 == 0:
+            partial[:] = False
+            partial[100:300] = True
+        muts = [types.SimpleNamespace(pos=start + int(p)) for p in np.flatnonzero(rng.random(n) < 0.01)]
+        hroi = types.SimpleNamespace(start=start, vcf_hook=True, mutations=muts,
+                                     p3_sequence_included_maps={"all": allm.copy(), "partial_mism": partial.copy(),
+                                                                "mism": mism.copy()})
+        lp.include_mut_in_included_maps(hroi)
+        before = {k2: [int(x) for x in np.flatnonzero(~v)] for k2, v in hroi.p3_sequence_included_maps.items()}
+        pcr_regions = {}
+        lp.get_sequence_excluded_regions(hroi)        # PCR / CAPS / HRM use the maps as they are
+        for k2, v in hroi.p3_sequence_excluded_regions.items():
+            pcr_regions[k2] = [[int(a), int(b)] for a, b in v]
+        # KASP: marker window (reference _lib_kasp.py:681-684, restated literally incl. its quirk)
+        for mmap in hroi.p3_sequence_included_maps.values():
+            s = np.min([1, (hroi.start - 25)])
+            e = np.max([len(mmap), (hroi.start + 25)])
+            mmap[s:e] = True
+        lp.get_sequence_excluded_regions(hroi)
+        kasp_regions = {k2: [[int(a), int(b)] for a, b in v] for k2, v in hroi.p3_sequence_excluded_regions.items()}
+        cases.append({"start": start, "n": n, "mism": [int(x) for x in np.flatnonzero(~mism)],
+                      "partial_mism": [int(x) for x in np.flatnonzero(~partial)],
+                      "mutation_pos": [int(m.pos) for m in muts], "excluded_idx_after_mut": before,
+                      "pcr_excluded_regions": pcr_regions, "kasp_excluded_regions": kasp_regions})
+    ivs = []
+    for _ in range(10):
+        m = int(rng.integers(150, 400))
+        starts = np.sort(rng.choice(5000, m, replace=False))
+        iv = [[int(s), int(rng.integers(1, 6))] for s in starts]
+        red = lu.reduce_ivs([list(x) for x in iv], n=200)
+        ivs.append({"in": iv, "out": [[int(a), int(b)] for a, b in red]})
+    dump("masks.json", {"cases": cases, "reduce_ivs": ivs})
+
+
+if __name__ == "__main__":
+    rng = np.random.default_rng(20240608)
+    golden_marker_primers(rng)
+    golden_is_valid(rng)
+    golden_heterodimer(rng)
+    golden_scoring(rng)
+    golden_masks(rng)
