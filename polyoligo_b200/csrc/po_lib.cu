@@ -7,6 +7,7 @@
 #include <cmath>
 #include <mutex>
 #include <string>
+#include <type_traits>
 
 #include "po_common.h"
 #include "po_thal.cuh"
@@ -35,12 +36,13 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
        const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
        const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax) {
+    using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem);
-    WarpWs<CAP>* wsAll = reinterpret_cast<WarpWs<CAP>*>(smem + sizeof(SmemTables));
+    Ws* wsAll = reinterpret_cast<Ws*>(smem + sizeof(SmemTables));
     stage_tables(tb, gt);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpWs<CAP>& ws = wsAll[warp];
+    Ws& ws = wsAll[warp];
     const unsigned long long total = list ? *list_n : (unsigned long long)n;
     for (;;) {
         unsigned long long t = 0;
@@ -50,7 +52,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
         const long long item = list ? list[t] : (long long)t;
         const uint4 oa = A[item];
         // upper bound of the finite-cell count: exact count is cheap from base composition
-        if (HAIRPIN) {
+        if constexpr (HAIRPIN) {
             int a, c, g, t_;
             po_base_counts(oa, po_len(oa), a, c, g, t_);
             const int ub = a * t_ + c * g;
@@ -349,7 +351,8 @@ template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
 static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4* B, long long n, po_thal_out* out,
                        unsigned long long* work, const long long* list, const unsigned long long* list_n,
                        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax) {
-    const size_t smem = sizeof(SmemTables) + WARPS * sizeof(WarpWs<CAP>);
+    using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
+    const size_t smem = sizeof(SmemTables) + WARPS * sizeof(Ws);
     auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -371,36 +374,42 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
     return PO_OK;
 }
 
-// two passes: a small-CAP pass with high occupancy, then a full-capacity pass
-// over whatever overflowed (repetitive / low-complexity inputs)
+// Capacity tiers.  The first pass keeps the per-warp shared-memory workspace
+// small (random 18-30 nt pairs have ~144 finite cells, <0.02% exceed 256) so
+// that 24-32 warps are resident per SM; items that exceed a tier's capacity are
+// queued for the next one (reporter-tailed KASP pairs, then low-complexity /
+// 60-mer inputs whose DP table is dense).  Counters: ctr[0] work1, ctr[1]
+// list1_n, ctr[2] work2, ctr[3] list2_n, ctr[4] work3, ctr[5] unused, ctr[7] relaxations.
 template <bool COUNT>
 static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out, cudaStream_t st) {
     if (n == 0) return PO_OK;
-    int rc = ensure(ctx, ctx->overflow, sizeof(long long) * (size_t)n);
+    int rc = ensure(ctx, ctx->overflow, 2 * sizeof(long long) * (size_t)n);
     if (rc) return rc;
     unsigned long long* ctr = ctx->d_ctr;
-    CK(cudaMemsetAsync(ctr, 0, 5 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctr, 0, 6 * sizeof(unsigned long long), st));
     const uint4* A = (const uint4*)d_a;
     const uint4* B = (const uint4*)d_b;
     po_thal_out* out = (po_thal_out*)d_out;
-    long long* ovf = (long long*)ctx->overflow.p;
-    const int cap = ctx->fast_cap ? ctx->fast_cap : 512;
+    long long* l1 = (long long*)ctx->overflow.p;
+    long long* l2 = l1 + n;
+    unsigned long long* rx = ctr + 7;
+    const int cap = ctx->fast_cap;
     if (type == PO_THAL_HAIRPIN) {
-        if (cap <= 256) rc = launch_thal<256, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
-        else if (cap <= 512) rc = launch_thal<512, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
-        else rc = launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+        if (cap == 256) rc = launch_thal<256, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+        else rc = launch_thal<128, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
         if (rc) return rc;
-        return launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 2, ovf, ctr + 1, ovf, ctr + 4, ctr + 7);
+        return launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx);
     }
     if (type != PO_THAL_ANY) {
         ctx->err = "po_thal: only PO_THAL_ANY and PO_THAL_HAIRPIN are implemented on the device";
         return PO_E_INVALID;
     }
-    if (cap <= 256) rc = launch_thal<256, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
-    else if (cap <= 512) rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
-    else rc = launch_thal<1024, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, ovf, ctr + 1, ctr + 7);
+    if (cap == 192) rc = launch_thal<192, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+    else if (cap == 320) rc = launch_thal<320, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+    else rc = launch_thal<256, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
     if (rc) return rc;
-    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, ovf, ctr + 1, ovf, ctr + 4, ctr + 7);
+    if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx))) return rc;
+    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx);
 }
 
 extern "C" int po_thal_batch_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out,
