@@ -39,8 +39,11 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
     using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem);
-    Ws* wsAll = reinterpret_cast<Ws*>(smem + sizeof(SmemTables));
+    SmemExtra* xt = reinterpret_cast<SmemExtra*>(smem + sizeof(SmemTables));
+    Ws* wsAll = reinterpret_cast<Ws*>(smem + sizeof(SmemTables) + sizeof(SmemExtra));
     stage_tables(tb, gt);
+    fill_extra(xt, *tb, K);
+    const TabAddr TA = tab_addr(*tb, *xt);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Ws& ws = wsAll[warp];
     const unsigned long long total = list ? *list_n : (unsigned long long)n;
@@ -60,7 +63,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                 if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
                 continue;
             }
-            thal_hairpin_warp<CAP, COUNT>(*tb, gt, ws, oa, K, out + item, relax);
+            thal_hairpin_warp<CAP, COUNT>(*tb, *xt, TA, gt, ws, oa, K, out + item, relax);
         } else {
             const uint4 ob = B ? B[item] : oa;
             int a1, c1, g1, t1, a2, c2, g2, t2;
@@ -71,7 +74,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                 if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
                 continue;
             }
-            thal_dimer_warp<CAP, COUNT>(*tb, ws, oa, ob, K, out + item, relax);
+            thal_dimer_warp<CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, out + item, relax);
         }
     }
 }
@@ -352,7 +355,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
                        unsigned long long* work, const long long* list, const unsigned long long* list_n,
                        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax) {
     using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
-    const size_t smem = sizeof(SmemTables) + WARPS * sizeof(Ws);
+    const size_t smem = sizeof(SmemTables) + sizeof(SmemExtra) + WARPS * sizeof(Ws);
     auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -395,8 +398,8 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
     unsigned long long* rx = ctr + 7;
     const int cap = ctx->fast_cap;
     if (type == PO_THAL_HAIRPIN) {
-        if (cap == 256) rc = launch_thal<256, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
-        else rc = launch_thal<128, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+        if (cap == 256) rc = launch_thal<256, 12, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+        else rc = launch_thal<128, 12, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
         if (rc) return rc;
         return launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx);
     }
@@ -404,9 +407,9 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
         ctx->err = "po_thal: only PO_THAL_ANY and PO_THAL_HAIRPIN are implemented on the device";
         return PO_E_INVALID;
     }
-    if (cap == 192) rc = launch_thal<192, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
-    else if (cap == 320) rc = launch_thal<320, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
-    else rc = launch_thal<256, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+    if (cap == 192) rc = launch_thal<192, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+    else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+    else rc = launch_thal<256, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
     if (rc) return rc;
     if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx))) return rc;
     return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx);

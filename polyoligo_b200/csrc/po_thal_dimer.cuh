@@ -1,55 +1,33 @@
 // po_thal_dimer.cuh -- thal type ANY (calcHomodimer / calcHeterodimer) for one
 // warp.  Restates upstream thal.c: initMatrix, fillMatrix (LSH, maxTM,
 // calc_bulge_internal), the RSH end scan, traceback and drawDimer.
+//
+// Control flow is kept warp-uniform (loops run a uniform number of trips with
+// clamped indices and predicated stores): a lane that leaves a loop early would
+// spin on the next warp barrier and burn issue slots.
 #pragma once
 #include "po_thal.cuh"
 
-// per-cell constants of the loop term (the side of the loop closed by the cell)
 struct DimerCellCtx {
-    int ci, cj, cb, c2;
-    double2 tsB;   // tstack   [s2[cj]][s2[cj-1]][s1[ci]][s1[ci-1]]
-    double2 x2B;   // stackint2, same index
-    double2 atC;   // AT penalty of the cell's own pair
+    int ci, cj;
+    int b1q;  // cb * 16 + c2: cell part of the bulge-of-one stack index
 };
-
-template <int CAP>
-__device__ __forceinline__ DimerCellCtx dimer_cell_ctx(const SmemTables& tb, const DimerWs<CAP>& ws, int ci, int cj) {
-    DimerCellCtx c;
-    c.ci = ci;
-    c.cj = cj;
-    c.cb = ws.s1[ci];
-    c.c2 = ws.s2[cj];
-    const int q = quad(c.c2, ws.s2[cj - 1], c.cb, ws.s1[ci - 1]);
-    c.tsB = tb.tstack[q];
-    c.x2B = tb.stackint2[q];
-    c.atC = make_double2(at_h(c.cb, c.c2), at_s(c.cb, c.c2));
-    return c;
-}
 
 // upstream calc_bulge_internal(pi, pj, ci, cj): value {dH,dS} of reaching the
 // cell through the loop that starts at list entry kp; {inf,-1} when rejected.
 template <int CAP>
-__device__ __forceinline__ double2 dimer_loop_value(const SmemTables& tb, const DimerWs<CAP>& ws,
-                                                    const DimerCellCtx& c, int kp, int* key_out) {
+__device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const DimerWs<CAP>& ws, const DimerCellCtx& c,
+                                                    int kp, int* key_out) {
     const uint32_t code = ws.code[kp];
     const double2 pv = ws.cell[kp];
-    const int pi = CODE_I(code), pj = CODE_J(code), pb = CODE_B(code);
-    const int l1 = c.ci - pi - 1, l2 = c.cj - pj - 1;
-    *key_out = KEY_OF(l1 + l2, l1);
-    const LoopSel s = loop_sel(l1, l2);
-    const double2 L = loop_L(tb, s);
-    // X: stack (bulge of one) | stackint2 (1x1) | tstack (interior), contiguous tables
-    const int xi = s.isB1 ? quad(pb, c.cb, 3 - pb, c.c2)
-                          : (s.isX ? 256 : 512) + quad(pb, CODE_N1(code), 3 - pb, CODE_N2(code));
-    double2 X = tb.stack[xi];
-    const bool pAT = (pb == 0) | (pb == 3);
-    if (s.isB & !s.isB1) X = make_double2(pAT ? PO_AT_H : 0.0, pAT ? PO_AT_S : 0.0);
-    double2 Y = s.isX ? c.x2B : c.tsB;
-    if (s.isB) Y = c.atC;
-    if (s.isB1) Y = make_double2(0.0, 0.0);
-    double H = (L.x + X.x) + Y.x;
-    double S = ((L.y + X.y) + Y.y) + (ILAS_D * s.asym);
-    if (s.isB1 & ((H > 0) | (S > 0))) {
+    const int pb = CODE_B(code);
+    const int l1 = c.ci - CODE_I(code) - 1, l2 = c.cj - CODE_J(code) - 1;
+    // stack[s1[pi]][s1[ci]][s2[pj]][s2[cj]] = pb*64 + cb*16 + (3-pb)*4 + c2
+    const LoopOps o = loop_ops(A, ws.ycell, l1, l2, CODE_TQ(code), pb, pb * 60 + 12 + c.b1q);
+    *key_out = o.key;
+    double H = (o.L.x + o.P.x) + o.C.x;
+    double S = ((o.L.y + o.P.y) + o.C.y) + o.asymS;
+    if (o.isB1 & ((H > 0) | (S > 0))) {
         H = PO_INF;
         S = -1.0;
     }
@@ -59,7 +37,7 @@ __device__ __forceinline__ double2 dimer_loop_value(const SmemTables& tb, const 
         H = PO_INF;
         S = -1.0;
     }
-    if (!s.isB1 & (H > 0) & (S > 0)) {
+    if (!o.isB1 & (H > 0) & (S > 0)) {
         H = PO_INF;
         S = -1.0;
     }
@@ -68,41 +46,58 @@ __device__ __forceinline__ double2 dimer_loop_value(const SmemTables& tb, const 
 
 // Candidate predecessors of cell (ci,cj): every finite (pi,pj) with pi < ci,
 // pj < cj and 1 <= (ci-pi-1)+(cj-pj-1) <= max_loop.  Lane l owns row ci-1-l;
-// the row's candidates are one contiguous run of the row-major list.
+// the row's candidates are one contiguous run of the row-major list.  Also
+// publishes the cell-side loop operands (ycell).  Returns the queue length.
 template <int CAP>
-__device__ __forceinline__ int dimer_build_queue(DimerWs<CAP>& ws, int lane, int ci, int cj, int max_loop) {
+__device__ __forceinline__ int dimer_build_queue(const SmemTables& tb, DimerWs<CAP>& ws, int lane, int ci, int cj,
+                                                 int max_loop, DimerCellCtx* ctx) {
     const int l1 = lane, r = ci - 1 - lane;
-    int cnt = 0, first = 0;
-    if (r >= 1 && l1 <= max_loop) {
-        const int hi_col = (l1 == 0) ? cj - 2 : cj - 1;           // l1 + l2 >= 1
-        const int lo_col = max(1, cj - 1 - (max_loop - l1));      // l1 + l2 <= max_loop
-        const unsigned long long rm = ws.mask[3 - ws.s1[r]];
-        cnt = __popcll(rm & bit_range(lo_col - 1, hi_col - 1));
-        first = ws.start[r] + __popcll(rm & bit_range(0, lo_col - 2));
-    }
+    const bool have = (r >= 1) & (l1 <= max_loop);
+    const int rr = have ? r : 1;
+    const int hi_col = (l1 == 0) ? cj - 2 : cj - 1;       // l1 + l2 >= 1
+    const int lo_col = max(1, cj - 1 - (max_loop - l1));  // l1 + l2 <= max_loop
+    const unsigned long long rm = ws.mask[3 - ws.s1[rr]];
+    const int cnt = have ? __popcll(rm & bit_range(lo_col - 1, hi_col - 1)) : 0;
+    const int first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
     const int incl = warp_scan_incl(cnt, lane);
     const int total = __shfl_sync(FULL, incl, 31);
-    int off = incl - cnt;
-    for (int q = 0; q < cnt; ++q) ws.queue[off + q] = (uint16_t)(first + q);
+    const int mx = __reduce_max_sync(FULL, cnt);
+    const int off = incl - cnt;
+    for (int q = 0; q < mx; ++q)
+        if (q < cnt) ws.queue[off + q] = (uint16_t)(first + q);
+    const int cb = ws.s1[ci], c2 = ws.s2[cj];
+    if (lane < 4) {
+        const int q = quad(c2, ws.s2[cj - 1], cb, ws.s1[ci - 1]);
+        double2 y = make_double2(0.0, 0.0);
+        if (lane == 0) y = tb.tstack[q];
+        if (lane == 1) y = make_double2(at_h(cb, c2), at_s(cb, c2));
+        if (lane == 3) y = tb.stackint2[q];
+        ws.ycell[lane] = y;
+    }
+    ctx->ci = ci;
+    ctx->cj = cj;
+    ctx->b1q = cb * 16 + c2;
     __syncwarp();
     return total;
 }
 
 // Forward scan of the queue: every lane keeps its best (largest T, earliest key).
 template <int CAP>
-__device__ __forceinline__ void dimer_scan(const SmemTables& tb, const DimerWs<CAP>& ws, const DimerCellCtx& c,
-                                           int lane, int total, double iH, double iS, double RC, int mode, double* bT,
-                                           int* bKey, double2* bV) {
+__device__ __forceinline__ void dimer_scan(const TabAddr& A, const DimerWs<CAP>& ws, const DimerCellCtx& c, int lane,
+                                           int total, double iH, double iS, double RC, int mode, double* bT, int* bKey,
+                                           double2* bV) {
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 bestV = make_double2(PO_INF, -1.0);
-    for (int t = lane; t < total; t += 32) {
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        bool act = t < total;
         int key;
-        const double2 v = dimer_loop_value<CAP>(tb, ws, c, ws.queue[t], &key);
-        if (mode == SCAN_NO_STAR && key == KEY_STAR) continue;
-        if (mode == SCAN_BEFORE_STAR && key >= KEY_STAR) continue;
+        const double2 v = dimer_loop_value<CAP>(A, ws, c, ws.queue[act ? t : 0], &key);
+        if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
+        if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double T1 = (v.x + iH) / ((v.y + iS) + RC);
-        if (T1 > bestT || (T1 == bestT && key < bestKey)) {
+        if (act & ((T1 > bestT) | ((T1 == bestT) & (key < bestKey)))) {
             bestT = T1;
             bestKey = key;
             bestV = v;
@@ -114,8 +109,9 @@ __device__ __forceinline__ void dimer_scan(const SmemTables& tb, const DimerWs<C
 }
 
 template <int CAP, bool COUNT>
-__device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const uint4 oa, const uint4 ob,
-                                const PoConsts& K, po_thal_out* out, unsigned long long* relax) {
+__device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const TabAddr& A, DimerWs<CAP>& ws,
+                                const uint4 oa, const uint4 ob, const PoConsts& K, po_thal_out* out,
+                                unsigned long long* relax) {
     const int lane = threadIdx.x & 31;
     const int len1 = po_len(oa), len2 = po_len(ob);
     po_thal_out r;
@@ -130,18 +126,24 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
     }
     __syncwarp();
     // ---- decode; the second oligo is reversed so it runs 3'->5' ------------
-    for (int p = lane; p < len1; p += 32) ws.s1[p + 1] = (uint8_t)po_base(oa, p);
-    for (int p = lane; p < len2; p += 32) ws.s2[len2 - p] = (uint8_t)po_base(ob, p);
+    for (int p = lane; p < 64; p += 32) {
+        if (p < len1) ws.s1[p + 1] = (uint8_t)po_base(oa, p);
+        if (p < len2) ws.s2[len2 - p] = (uint8_t)po_base(ob, p);
+    }
     if (lane == 0) {
         ws.s1[0] = ws.s1[len1 + 1] = 4;
         ws.s2[0] = ws.s2[len2 + 1] = 4;
     }
     // upstream symmetry_thermo() on both oligos
     bool asym = false;
-    for (int p = lane; p < len1 / 2; p += 32) asym |= (po_base(oa, p) + po_base(oa, len1 - 1 - p) != 3);
-    for (int p = lane; p < len2 / 2; p += 32) asym |= (po_base(ob, p) + po_base(ob, len2 - 1 - p) != 3);
+    for (int p = lane; p < 32; p += 32) {
+        if (p < len1 / 2) asym |= (po_base(oa, p) + po_base(oa, len1 - 1 - p) != 3);
+        if (p < len2 / 2) asym |= (po_base(ob, p) + po_base(ob, len2 - 1 - p) != 3);
+    }
     const bool sym = !__any_sync(FULL, asym) && (len1 % 2 == 0) && (len2 % 2 == 0);
     const double RC = sym ? K.rc_sym : K.rc_nonsym;
+    const double2* lshT = X.lsh[sym ? 1 : 0];
+    const double2* rshT = X.rsh[sym ? 1 : 0];
     const double iH = 200.0, iS = -5.7;
     const int max_loop = K.max_loop;
     __syncwarp();
@@ -155,6 +157,8 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
     }
     __syncwarp();
 #define ROWMASK(i) (ws.mask[3 - ws.s1[i]])
+#define LSH_AT(i, j) (lshT[END_IDX(ws.s1[i], ws.s1[(i)-1], ws.s2[(j)-1])])
+#define RSH_AT(i, j) (rshT[END_IDX(ws.s1[i], ws.s1[(i) + 1], ws.s2[(j) + 1])])
     // row starts (exclusive prefix of per-row popcounts), two rows per lane
     {
         const int i0 = lane + 1, i1 = lane + 33;
@@ -170,13 +174,16 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
     for (int i = 1; i <= len1; ++i) {
         const unsigned long long m = ROWMASK(i);
         const int base = ws.start[i];
-        const uint32_t rowcode = (uint32_t)i | ((uint32_t)ws.s1[i] << 12) | ((uint32_t)(ws.s1[i + 1] & 3) << 14);
+        const int a = ws.s1[i], an = ws.s1[i + 1] & 3;
+        const uint32_t rowcode = (uint32_t)i | ((uint32_t)a << 20);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int bit = lane + 32 * h;  // column j = bit + 1
-            if ((m >> bit) & 1ull)
+            if ((m >> bit) & 1ull) {
+                const int tq = quad(a, an, 3 - a, ws.s2[bit + 2] & 3);
                 ws.code[base + __popcll(m & ((1ull << bit) - 1ull))] =
-                    rowcode | ((uint32_t)(bit + 1) << 6) | ((uint32_t)(ws.s2[bit + 2] & 3) << 16);
+                    rowcode | ((uint32_t)(bit + 1) << 6) | ((uint32_t)tq << 12);
+            }
         }
     }
     __syncwarp();
@@ -187,29 +194,29 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
         const int rs = ws.start[i], re = ws.start[i + 1];
         if (rs == re) continue;
         // phase A: LSH seed and maxTM (stack) for every finite cell of the row
-        for (int k = rs + lane; k < re; k += 32) {
+        for (int k0 = rs; k0 < re; k0 += 32) {
+            const bool act = k0 + lane < re;
+            const int k = act ? k0 + lane : re - 1;
             const int j = CODE_J(ws.code[k]);
-            double2 v = lsh(tb, ws.s1, ws.s2, i, j, iH, iS, RC);
-            if (COUNT) ++cnt;
+            double2 v = LSH_AT(i, j);
+            if (COUNT) cnt += act ? 1 : 0;
             if (i > 1 && j > 1) {
-                if (COUNT) ++cnt;
-                double S0 = v.y, H0 = v.x;
-                const double2 sh = rsh(tb, ws.s1, ws.s2, i, j, iH, iS, RC);
+                if (COUNT) cnt += act ? 1 : 0;
+                const double S0 = v.y, H0 = v.x;
+                const double2 sh = RSH_AT(i, j);
                 const double T0 = (H0 + iH + sh.x) / (S0 + iS + RC + sh.y);
-                double S1 = -1.0, H1 = PO_INF, T1;
+                double S1 = -1.0, H1 = PO_INF;
                 const unsigned long long pm = ROWMASK(i - 1);
-                bool have = false;
-                if ((pm >> (j - 2)) & 1ull) {
-                    const double2 pv = ws.cell[ws.start[i - 1] + __popcll(pm & ((1ull << (j - 2)) - 1ull))];
-                    const double2 st = tb.stack[quad(ws.s1[i - 1], ws.s1[i], ws.s2[j - 1], ws.s2[j])];
-                    if (fin(pv.x) && fin(st.x)) {
-                        S1 = pv.y + st.y;
-                        H1 = pv.x + st.x;
-                        have = true;
-                    }
+                const bool pfin = (pm >> (j - 2)) & 1ull;
+                const int kp = pfin ? ws.start[i - 1] + __popcll(pm & ((1ull << (j - 2)) - 1ull)) : 0;
+                const double2 pv = ws.cell[kp];
+                const double2 st = tb.stack[quad(ws.s1[i - 1], ws.s1[i], ws.s2[j - 1], ws.s2[j])];
+                const bool have = pfin && fin(pv.x) && fin(st.x);
+                if (have) {
+                    S1 = pv.y + st.y;
+                    H1 = pv.x + st.x;
                 }
-                if (have) T1 = (H1 + iH + sh.x) / (S1 + iS + RC + sh.y);
-                else T1 = (H1 + iH) / (S1 + iS + RC);
+                const double T1 = have ? (H1 + iH + sh.x) / (S1 + iS + RC + sh.y) : (H1 + iH) / (S1 + iS + RC);
                 if (S1 < PO_MIN_ENTROPY_CUTOFF) {
                     S1 = PO_MIN_ENTROPY;
                     H1 = 0.0;
@@ -222,7 +229,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
                 if (T1 > T0) v = make_double2(H1, S1);
                 else if (T0 >= T1) v = make_double2(H0c, S0c);
             }
-            ws.cell[k] = v;
+            if (act) ws.cell[k] = v;
         }
         __syncwarp();
         if (i == 1) continue;
@@ -230,16 +237,16 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
         for (int k = rs; k < re; ++k) {
             const int j = CODE_J(ws.code[k]);
             if (j == 1) continue;
-            const int total = dimer_build_queue<CAP>(ws, lane, i, j, max_loop);
+            DimerCellCtx c;
+            const int total = dimer_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
             if (COUNT) cnt += (lane == 0) ? total : 0;
             if (total == 0) continue;
-            const DimerCellCtx c = dimer_cell_ctx<CAP>(tb, ws, i, j);
             const double2 cur = ws.cell[k];
             const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
-            double bT, wT;
-            int bKey, wKey;
+            double bT, wT = -PO_INF;
+            int bKey, wKey = KEY_NONE;
             double2 bV;
-            dimer_scan<CAP>(tb, ws, c, lane, total, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
+            dimer_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
             int src = warp_argmax(bT, bKey, &wT, &wKey);
             if (src >= 0 && wKey == KEY_STAR) {
                 // The 1x1 loop is the arg-max.  Upstream accepts it only if it beats the
@@ -248,11 +255,11 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
                 double pT, qT = -PO_INF;
                 int pKey, qKey = KEY_NONE;
                 double2 pV;
-                dimer_scan<CAP>(tb, ws, c, lane, total, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
+                dimer_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
                 const int psrc = warp_argmax(pT, pKey, &qT, &qKey);
                 const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
                 if (!((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm)) {
-                    dimer_scan<CAP>(tb, ws, c, lane, total, iH, iS, RC, SCAN_NO_STAR, &bT, &bKey, &bV);
+                    dimer_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_NO_STAR, &bT, &bKey, &bV);
                     src = warp_argmax(bT, bKey, &wT, &wKey);
                 }
             }
@@ -271,14 +278,16 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
     // ---- end scan: minimum dG over all cells, first in row-major order wins ---
     double bestG = PO_INF;
     int bestK = KEY_NONE;
-    for (int k = lane; k < ncell; k += 32) {
+    for (int k0 = 0; k0 < ncell; k0 += 32) {
+        const bool act = k0 + lane < ncell;
+        const int k = act ? k0 + lane : 0;
         const uint32_t code = ws.code[k];
         const double2 v = ws.cell[k];
-        double2 sh = rsh(tb, ws.s1, ws.s2, CODE_I(code), CODE_J(code), iH, iS, RC);
+        double2 sh = RSH_AT(CODE_I(code), CODE_J(code));
         sh.y = sh.y + PO_SMALL_NON_ZERO;
         sh.x = sh.x + PO_SMALL_NON_ZERO;
         const double G1 = (v.x + sh.x + iH) - PO_TEMP_KELVIN * (v.y + sh.y + iS);
-        if (G1 < bestG) {
+        if (act & (G1 < bestG)) {
             bestG = G1;
             bestK = k;
         }
@@ -301,7 +310,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
     double dH, dS;
     {
         const double2 v = ws.cell[wK];
-        const double2 sh = rsh(tb, ws.s1, ws.s2, i, j, iH, iS, RC);
+        const double2 sh = RSH_AT(i, j);
         dH = v.x + sh.x + iH;
         dS = v.y + sh.y + iS;
     }
@@ -312,7 +321,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
         const unsigned long long rm = ROWMASK(i);
         const int k = ws.start[i] + __popcll(rm & ((1ull << (j - 1)) - 1ull));
         const double2 cur = ws.cell[k];
-        const double2 l = lsh(tb, ws.s1, ws.s2, i, j, iH, iS, RC);
+        const double2 l = LSH_AT(i, j);
         if (eq5(cur.y, l.y) && eq5(cur.x, l.x)) break;
         if (i == 1 || j == 1) break;  // guard: nothing can precede the first row / column
         {
@@ -330,18 +339,18 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
         }
         // loops: first candidate in upstream order whose value reproduces the cell
         const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
-        const int total = dimer_build_queue<CAP>(ws, lane, i, j, max_loop);
-        const DimerCellCtx c = dimer_cell_ctx<CAP>(tb, ws, i, j);
+        DimerCellCtx c;
+        const int total = dimer_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
         int myKey = KEY_NONE;
-        for (int t = lane; t < total; t += 32) {
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            const bool act = t < total;
             int key;
-            const double2 v = dimer_loop_value<CAP>(tb, ws, c, ws.queue[t], &key);
-            if (key >= myKey) continue;
-            if (key == KEY_STAR) {  // traceback mode of the 1x1 branch: only when T1 >= T2
-                const double T1 = (v.x + iH) / ((v.y + iS) + RC);
-                if (!(T1 >= Tcur)) continue;
-            }
-            if (eq5(cur.y, v.y) && eq5(cur.x, v.x)) myKey = key;
+            const double2 v = dimer_loop_value<CAP>(A, ws, c, ws.queue[act ? t : 0], &key);
+            const double T1 = (v.x + iH) / ((v.y + iS) + RC);
+            // traceback mode of the 1x1 branch reports its value only when T1 >= T2
+            const bool ok = act & (key < myKey) & ((key != KEY_STAR) | (T1 >= Tcur));
+            if (ok && eq5(cur.y, v.y) && eq5(cur.x, v.x)) myKey = key;
         }
         const int wKey = warp_min_int(myKey);
         __syncwarp();
@@ -352,6 +361,8 @@ __device__ void thal_dimer_warp(const SmemTables& tb, DimerWs<CAP>& ws, const ui
         ++npairs;
     }
 #undef ROWMASK
+#undef LSH_AT
+#undef RSH_AT
 
     // ---- drawDimer ---------------------------------------------------------------
     const int N = npairs - 1;  // (2 * npairs) / 2 - 1

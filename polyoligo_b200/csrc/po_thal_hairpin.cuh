@@ -5,7 +5,8 @@
 //
 // Finite cells (i,j): j - i >= 4 and bases complementary.  They are kept in
 // upstream's fill order (j ascending, i descending), so the cells enclosed by
-// (i,j) are a prefix of the list.
+// (i,j) are a prefix of the list.  Control flow is kept warp-uniform (see
+// po_thal_dimer.cuh).
 #pragma once
 #include "po_thal.cuh"
 
@@ -13,52 +14,26 @@
 #define HP_COLMASK(ws, j) ((j) >= 5 ? ((ws).mask[3 - (ws).s1[j]] & ((1ull << ((j)-4)) - 1ull)) : 0ull)
 
 struct HairpinCellCtx {
-    int i, j, bi, bj;
-    double2 tsC;  // tstack   [s[i]][s[i+1]][s[j]][s[j-1]]
-    double2 x2C;  // stackint2, same index
-    double2 atC;  // AT penalty of the closing pair
+    int i, j;
+    int b1q;  // bi * 64 + bj * 4: closing-pair part of the bulge-of-one stack index
 };
-
-template <int CAP>
-__device__ __forceinline__ HairpinCellCtx hairpin_cell_ctx(const SmemTables& tb, const HairpinWs<CAP>& ws, int i,
-                                                           int j) {
-    HairpinCellCtx c;
-    c.i = i;
-    c.j = j;
-    c.bi = ws.s1[i];
-    c.bj = ws.s1[j];
-    const int q = quad(c.bi, ws.s1[i + 1], c.bj, ws.s1[j - 1]);
-    c.tsC = tb.tstack[q];
-    c.x2C = tb.stackint2[q];
-    c.atC = make_double2(at_h(c.bi, c.bj), at_s(c.bi, c.bj));
-    return c;
-}
 
 // upstream calc_bulge_internal2(i, j, ii, jj) WITHOUT the enclosed cell's own
 // value (its traceback == 1 form); the forward pass adds that value afterwards
-// in the same association order.
+// in the same association order.  In upstream's sums the closing pair's term
+// comes first, the enclosed pair's second.
 template <int CAP>
-__device__ __forceinline__ double2 hairpin_loop_term(const SmemTables& tb, const HairpinWs<CAP>& ws,
+__device__ __forceinline__ double2 hairpin_loop_term(const TabAddr& A, const HairpinWs<CAP>& ws,
                                                      const HairpinCellCtx& c, int kp, int* key_out) {
     const uint32_t code = ws.code[kp];
-    const int ii = CODE_I(code), jj = CODE_J(code), b = CODE_B(code);
-    const int l1 = ii - c.i - 1, l2 = c.j - jj - 1;
-    *key_out = KEY_OF(l1 + l2, l1);
-    const LoopSel s = loop_sel(l1, l2);
-    const double2 L = loop_L(tb, s);
-    // one table load: stack (bulge of one) | stackint2 (1x1) | tstack (interior), enclosed-pair side
-    const int vi = s.isB1 ? quad(c.bi, b, c.bj, 3 - b)
-                          : (s.isX ? 256 : 512) + quad(3 - b, CODE_N2(code), b, CODE_N1(code));
-    const double2 V = tb.stack[vi];
-    double2 X = s.isX ? c.x2C : c.tsC;  // closing-pair side comes first in upstream's sums
-    if (s.isB) X = c.atC;
-    if (s.isB1) X = V;
-    const bool pAT = (b == 0) | (b == 3);
-    double2 Y = V;
-    if (s.isB) Y = make_double2(pAT ? PO_AT_H : 0.0, pAT ? PO_AT_S : 0.0);
-    if (s.isB1) Y = make_double2(0.0, 0.0);
-    const double H = (L.x + X.x) + Y.x;
-    const double S = ((L.y + X.y) + Y.y) + (ILAS_D * s.asym);
+    const int b = CODE_B(code);
+    const int l1 = CODE_I(code) - c.i - 1, l2 = c.j - CODE_J(code) - 1;
+    // stack[s[i]][s[ii]][s[j]][s[jj]] = bi*64 + b*16 + bj*4 + (3-b)
+    const LoopOps o = loop_ops(A, ws.ycell, l1, l2, CODE_TQ(code), b, c.b1q + b * 15 + 3);
+    *key_out = o.key;
+    // bulge of one: upstream sums bulge + stack only; otherwise closing side, then enclosed side
+    const double H = o.isB1 ? (o.L.x + o.P.x) + o.C.x : (o.L.x + o.C.x) + o.P.x;
+    const double S = (o.isB1 ? (o.L.y + o.P.y) + o.C.y : (o.L.y + o.C.y) + o.P.y) + o.asymS;
     return make_double2(H, S);
 }
 
@@ -89,8 +64,8 @@ __device__ __forceinline__ double2 hairpin_closure(const SmemTables& tb, const P
     const int li = loopSize <= 30 ? loopSize - 1 : 29;
     H = tb.hairpin[li].x;
     S = tb.hairpin[li].y;
+    const double2 t = tb.tstack2[quad(s[i], s[i + 1] & 3, s[j], s[j - 1] & 3)];
     if (loopSize > 3) {
-        const double2 t = tb.tstack2[quad(s[i], s[i + 1], s[j], s[j - 1])];
         H += t.x;
         S += t.y;
     } else if (loopSize == 3) {
@@ -140,24 +115,37 @@ __device__ __forceinline__ bool hp_finite(const HairpinWs<CAP>& ws, int i, int j
 
 // Candidates enclosed by (i,j): every finite (ii,jj) with i < ii, jj < j and
 // 1 <= (ii-i-1)+(j-jj-1) <= max_loop.  Lane l owns column j-1-l; the column's
-// candidates are one contiguous run of the list (rows descending).
+// candidates are one contiguous run of the list (rows descending).  Also
+// publishes the closing-pair loop operands (ycell).
 template <int CAP>
-__device__ __forceinline__ int hairpin_build_queue(HairpinWs<CAP>& ws, int lane, int i, int j, int max_loop) {
+__device__ __forceinline__ int hairpin_build_queue(const SmemTables& tb, HairpinWs<CAP>& ws, int lane, int i, int j,
+                                                   int max_loop, HairpinCellCtx* ctx) {
     const int l2 = lane, jj = j - 1 - lane;
-    int cnt = 0, first = 0;
-    if (jj >= 5 && l2 <= max_loop) {
-        const int lo_row = (l2 == 0) ? i + 2 : i + 1;            // l1 + l2 >= 1
-        const int hi_row = min(jj - 4, i + 1 + (max_loop - l2));  // l1 + l2 <= max_loop
-        if (hi_row >= lo_row) {
-            const unsigned long long cm = HP_COLMASK(ws, jj);
-            cnt = __popcll(cm & bit_range(lo_row - 1, hi_row - 1));
-            first = ws.start[jj] + __popcll(cm >> hi_row);
-        }
-    }
+    const bool have = (jj >= 5) & (l2 <= max_loop);
+    const int jc = have ? jj : 5;
+    const int lo_row = (l2 == 0) ? i + 2 : i + 1;            // l1 + l2 >= 1
+    const int hi_row = min(jc - 4, i + 1 + (max_loop - l2));  // l1 + l2 <= max_loop
+    const unsigned long long cm = HP_COLMASK(ws, jc);
+    const int cnt = have ? __popcll(cm & bit_range(lo_row - 1, hi_row - 1)) : 0;
+    const int first = ws.start[jc] + __popcll(hi_row >= 0 ? (cm >> min(hi_row, 63)) : cm);
     const int incl = warp_scan_incl(cnt, lane);
     const int total = __shfl_sync(FULL, incl, 31);
+    const int mx = __reduce_max_sync(FULL, cnt);
     const int off = incl - cnt;
-    for (int q = 0; q < cnt; ++q) ws.queue[off + q] = (uint16_t)(first + q);
+    for (int q = 0; q < mx; ++q)
+        if (q < cnt) ws.queue[off + q] = (uint16_t)(first + q);
+    const int bi = ws.s1[i], bj = ws.s1[j];
+    if (lane < 4) {
+        const int q = quad(bi, ws.s1[i + 1] & 3, bj, ws.s1[j - 1] & 3);
+        double2 y = make_double2(0.0, 0.0);
+        if (lane == 0) y = tb.tstack[q];
+        if (lane == 1) y = make_double2(at_h(bi, bj), at_s(bi, bj));
+        if (lane == 3) y = tb.stackint2[q];
+        ws.ycell[lane] = y;
+    }
+    ctx->i = i;
+    ctx->j = j;
+    ctx->b1q = bi * 64 + bj * 4;
     __syncwarp();
     return total;
 }
@@ -166,30 +154,29 @@ __device__ __forceinline__ int hairpin_build_queue(HairpinWs<CAP>& ws, int lane,
 // with T1 >= Tcur, which is what upstream's CBI(traceback = 2) leaves in its
 // output argument.
 template <int CAP>
-__device__ __forceinline__ void hairpin_scan(const SmemTables& tb, const HairpinWs<CAP>& ws, const HairpinCellCtx& c,
+__device__ __forceinline__ void hairpin_scan(const TabAddr& A, const HairpinWs<CAP>& ws, const HairpinCellCtx& c,
                                              int lane, int total, double iH, double iS, double RC, int mode,
                                              double Tcur, double* bT, int* bKey, double2* bV) {
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 bestV = make_double2(PO_INF, -1.0);
-    for (int t = lane; t < total; t += 32) {
-        const int kp = ws.queue[t];
+    for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        bool act = t < total;
+        const int kp = ws.queue[act ? t : 0];
         int key;
-        double2 v = hairpin_loop_term<CAP>(tb, ws, c, kp, &key);
-        if (mode == SCAN_NO_STAR && key == KEY_STAR) continue;
-        if (mode == SCAN_BEFORE_STAR && key >= KEY_STAR) continue;
+        double2 v = hairpin_loop_term<CAP>(A, ws, c, kp, &key);
+        if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
+        if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double2 pv = ws.cell[kp];
         v.x += pv.x;
         v.y += pv.y;
         v = hp_fix(v.x, v.y);
         const double T1 = (v.x + iH) / ((v.y + iS) + RC);
-        if (mode == SCAN_LAST_GE) {
-            if (T1 >= Tcur && (bestKey == KEY_NONE || key > bestKey)) {
-                bestT = T1;
-                bestKey = key;
-                bestV = v;
-            }
-        } else if (T1 > bestT || (T1 == bestT && key < bestKey)) {
+        bool take;
+        if (mode == SCAN_LAST_GE) take = act & (T1 >= Tcur) & ((bestKey == KEY_NONE) | (key > bestKey));
+        else take = act & ((T1 > bestT) | ((T1 == bestT) & (key < bestKey)));
+        if (take) {
             bestT = T1;
             bestKey = key;
             bestV = v;
@@ -212,63 +199,67 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 best = make_double2(PO_INF, -1.0);
-    if (q >= 5) {
-        const int ks = ws.start[q], ke = ws.start[q + 1];
-        const double T2 = (0 + iH) / (0 + iS + RC);
-        for (int kc = ks + sub; kc < ke; kc += 8) {
-            const int p = CODE_I(ws.code[kc]);
-            const int k = (v == 1 || v == 3) ? p - 1 : p - 2;  // the exterior prefix ends at k
-            if (k < 0) continue;
-            double2 x = make_double2(0.0, 0.0);
-            if (v == 2) x = tb.dangle5[(s[i] * 4 + s[k + 2]) * 4 + s[k + 1]];           // Hd5(i, k+2)
-            else if (v == 3) x = tb.dangle3[(s[i - 1] * 4 + s[i]) * 4 + s[k + 1]];      // Hd3(i-1, k+1)
-            else if (v == 4) x = tb.tstack2[quad(s[i - 1], s[i], s[k + 2], s[k + 1])];  // Htstack(i-1, k+2)
-            const double2 dv = ws.cell[kc];
-            const double hk = ws.end5[0][k], sk = ws.end5[1][k];
-            const double T1p = (hk + iH) / (sk + iS + RC);
-            double H, S;
-            const double aH = at_h(s[p], s[q]), aS = at_s(s[p], s[q]);
-            if (T1p >= T2) {
-                if (v == 1) {
-                    H = hk + aH + dv.x;
-                    S = sk + aS + dv.y;
-                } else {
-                    H = hk + aH + x.x + dv.x;
-                    S = sk + aS + x.y + dv.y;
-                }
+    // uniform trip count over both columns (i and i-1)
+    const int n_i = i >= 5 ? ws.start[i + 1] - ws.start[i] : 0;
+    const int n_im = i >= 6 ? ws.start[i] - ws.start[i - 1] : 0;
+    const int trips = (max(n_i, n_im) + 7) >> 3;
+    const int ks = q >= 5 ? ws.start[q] : 0, ke = q >= 5 ? ws.start[q + 1] : 0;
+    const double T2 = (0 + iH) / (0 + iS + RC);
+    for (int it = 0; it < trips; ++it) {
+        const int kc0 = ks + sub + 8 * it;
+        bool act = kc0 < ke;
+        const int kc = act ? kc0 : 0;
+        const int p = CODE_I(ws.code[kc]);
+        const int k = (v == 1 || v == 3) ? p - 1 : p - 2;  // the exterior prefix ends at k
+        act &= k >= 0;
+        const int kk = act ? k : 0;
+        const int bp = s[kk + 1] & 3, bp2 = s[kk + 2] & 3, bi = s[i] & 3, bim = s[i - 1] & 3;
+        double2 x = make_double2(0.0, 0.0);
+        if (v == 2) x = tb.dangle5[(bi * 4 + bp2) * 4 + bp];            // Hd5(i, k+2)
+        else if (v == 3) x = tb.dangle3[(bim * 4 + bi) * 4 + bp];       // Hd3(i-1, k+1)
+        else if (v == 4) x = tb.tstack2[quad(bim, bi, bp2, bp)];        // Htstack(i-1, k+2)
+        const double2 dv = ws.cell[kc];
+        const double hk = ws.end5[0][kk], sk = ws.end5[1][kk];
+        const double T1p = (hk + iH) / (sk + iS + RC);
+        double H, S;
+        const int pp = act ? p : 1, qq = act ? q : 1;
+        const double aH = at_h(s[pp], s[qq]), aS = at_s(s[pp], s[qq]);
+        if (T1p >= T2) {
+            if (v == 1) {
+                H = hk + aH + dv.x;
+                S = sk + aS + dv.y;
             } else {
-                if (v == 1) {
-                    H = 0 + aH + dv.x;
-                    S = 0 + aS + dv.y;
-                } else {
-                    H = 0 + aH + x.x + dv.x;
-                    S = 0 + aS + x.y + dv.y;
-                }
+                H = hk + aH + x.x + dv.x;
+                S = sk + aS + x.y + dv.y;
             }
-            if (!fin(H) || H > 0 || S > 0) {
-                H = PO_INF;
-                S = -1.0;
+        } else {
+            if (v == 1) {
+                H = 0 + aH + dv.x;
+                S = 0 + aS + dv.y;
+            } else {
+                H = 0 + aH + x.x + dv.x;
+                S = 0 + aS + x.y + dv.y;
             }
-            const double T1 = (H + iH) / (S + iS + RC);
-            if (!(S > PO_MIN_ENTROPY_CUTOFF)) continue;
-            // upstream keeps the first k with the strictly largest T1; -inf never wins
-            if (T1 > bestT || (T1 == bestT && k < bestKey)) {
-                if (T1 > -PO_INF) {
-                    bestT = T1;
-                    bestKey = k;
-                    best = make_double2(H, S);
-                }
-            }
+        }
+        if (!fin(H) || H > 0 || S > 0) {
+            H = PO_INF;
+            S = -1.0;
+        }
+        const double T1 = (H + iH) / (S + iS + RC);
+        // upstream keeps the first k with the strictly largest T1; -inf never wins
+        if (act & (S > PO_MIN_ENTROPY_CUTOFF) & (T1 > -PO_INF) & ((T1 > bestT) | ((T1 == bestT) & (k < bestKey)))) {
+            bestT = T1;
+            bestKey = k;
+            best = make_double2(H, S);
         }
     }
     // arg-max inside each 8-lane group
-    __syncwarp();
 #pragma unroll
     for (int m = 4; m >= 1; m >>= 1) {
         const double ot = shfl_xor_d(bestT, m);
         const int ok = __shfl_xor_sync(FULL, bestKey, m);
         const double oh = shfl_xor_d(best.x, m), os = shfl_xor_d(best.y, m);
-        if (ot > bestT || (ot == bestT && ok < bestKey)) {
+        if ((ot > bestT) | ((ot == bestT) & (ok < bestKey))) {
             bestT = ot;
             bestKey = ok;
             best = make_double2(oh, os);
@@ -278,8 +269,9 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
 }
 
 template <int CAP, bool COUNT>
-__device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, HairpinWs<CAP>& ws, const uint4 oa,
-                                  const PoConsts& K, po_thal_out* out, unsigned long long* relax) {
+__device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, const TabAddr& A, const PoTables* gt,
+                                  HairpinWs<CAP>& ws, const uint4 oa, const PoConsts& K, po_thal_out* out,
+                                  unsigned long long* relax) {
     const int lane = threadIdx.x & 31;
     const int len = po_len(oa);
     po_thal_out r;
@@ -293,9 +285,11 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
         return;
     }
     __syncwarp();
-    for (int p = lane; p < len; p += 32) ws.s1[p + 1] = (uint8_t)po_base(oa, p);
+    for (int p = lane; p < 64; p += 32)
+        if (p < len) ws.s1[p + 1] = (uint8_t)po_base(oa, p);
     if (lane == 0) ws.s1[0] = ws.s1[len + 1] = 4;
     const double iH = 0.0, iS = -0.00000000001, RC = 0.0;
+    const double2* rshT = X.rsh[2];
     const int max_loop = K.max_loop;
     __syncwarp();
 #pragma unroll
@@ -319,14 +313,17 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
     for (int j = 5; j <= len; ++j) {
         const unsigned long long m = HP_COLMASK(ws, j);
         const int base = ws.start[j];
-        const uint32_t colcode = ((uint32_t)j << 6) | ((uint32_t)(ws.s1[j + 1] & 3) << 16);
+        const int bj = ws.s1[j], bjn = ws.s1[j + 1] & 3;
+        const uint32_t colcode = ((uint32_t)j << 6);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int bit = lane + 32 * h;  // row i = bit + 1; list order is i descending
-            if ((m >> bit) & 1ull)
-                ws.code[base + __popcll(m >> (bit + 1))] = colcode | (uint32_t)(bit + 1) |
-                                                           ((uint32_t)ws.s1[bit + 1] << 12) |
-                                                           ((uint32_t)(ws.s1[bit] & 3) << 14);
+            if ((m >> bit) & 1ull) {
+                const int bi = ws.s1[bit + 1];
+                const int tq = quad(bj, bjn, bi, ws.s1[bit] & 3);  // [s[j]][s[j+1]][s[i]][s[i-1]]
+                ws.code[base + __popcll(m >> (bit + 1))] =
+                    colcode | (uint32_t)(bit + 1) | ((uint32_t)tq << 12) | ((uint32_t)bi << 20);
+            }
         }
     }
     __syncwarp();
@@ -337,12 +334,15 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
         const int cs = ws.start[j], ce = ws.start[j + 1];
         if (cs == ce) continue;
         // phase A: maxTM2 (stack on (i+1, j-1)) for every finite cell of the column
-        for (int k = cs + lane; k < ce; k += 32) {
+        for (int k0 = cs; k0 < ce; k0 += 32) {
+            const bool act = k0 + lane < ce;
+            const int k = act ? k0 + lane : ce - 1;
             const int i = CODE_I(ws.code[k]);
             double S0 = PO_MIN_ENTROPY, H0 = 0.0;
             const double T0 = (H0 + iH) / (S0 + iS + RC);
-            double2 pv = make_double2(PO_INF, -1.0);
-            if (hp_finite<CAP>(ws, i + 1, j - 1)) pv = ws.cell[hp_index<CAP>(ws, i + 1, j - 1)];
+            const bool pfin = hp_finite<CAP>(ws, i + 1, j - 1);
+            double2 pv = ws.cell[pfin ? hp_index<CAP>(ws, i + 1, j - 1) : 0];
+            if (!pfin) pv = make_double2(PO_INF, -1.0);
             const double2 st = tb.stack[quad(ws.s1[i], ws.s1[i + 1], ws.s1[j], ws.s1[j - 1])];
             double S1 = pv.y + st.y;
             double H1 = pv.x + st.x;
@@ -355,33 +355,33 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
                 S0 = PO_MIN_ENTROPY;
                 H0 = 0.0;
             }
-            ws.cell[k] = (T1 > T0) ? make_double2(H1, S1) : make_double2(H0, S0);
+            if (act) ws.cell[k] = (T1 > T0) ? make_double2(H1, S1) : make_double2(H0, S0);
         }
         __syncwarp();
         // phase B: CBI, one cell at a time
         for (int k = cs; k < ce; ++k) {
             const int i = CODE_I(ws.code[k]);
             if (j - i < 7) continue;  // no room for an enclosed pair plus a loop
-            const int total = hairpin_build_queue<CAP>(ws, lane, i, j, max_loop);
+            HairpinCellCtx c;
+            const int total = hairpin_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
             if (COUNT) cnt += (lane == 0) ? total : 0;
             if (total == 0) continue;
-            const HairpinCellCtx c = hairpin_cell_ctx<CAP>(tb, ws, i, j);
             const double2 cur = ws.cell[k];
             const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
             double bT, wT = -PO_INF;
             int bKey, wKey = KEY_NONE;
             double2 bV;
-            hairpin_scan<CAP>(tb, ws, c, lane, total, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
+            hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
             int src = warp_argmax(bT, bKey, &wT, &wKey);
             if (src >= 0 && wKey == KEY_STAR) {
                 double pT, qT = -PO_INF;
                 int pKey, qKey = KEY_NONE;
                 double2 pV;
-                hairpin_scan<CAP>(tb, ws, c, lane, total, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey, &pV);
+                hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey, &pV);
                 const int psrc = warp_argmax(pT, pKey, &qT, &qKey);
                 const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
                 if (!((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm)) {
-                    hairpin_scan<CAP>(tb, ws, c, lane, total, iH, iS, RC, SCAN_NO_STAR, Tcur, &bT, &bKey, &bV);
+                    hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_NO_STAR, Tcur, &bT, &bKey, &bV);
                     src = warp_argmax(bT, bKey, &wT, &wKey);
                 }
             }
@@ -398,18 +398,20 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
             __syncwarp();
         }
         // phase C: calc_hairpin, keep the lower dG of {loop closure, current value}
-        for (int k = cs + lane; k < ce; k += 32) {
+        for (int k0 = cs; k0 < ce; k0 += 32) {
+            const bool act = k0 + lane < ce;
+            const int k = act ? k0 + lane : ce - 1;
             const int i = CODE_I(ws.code[k]);
             const double2 cur = ws.cell[k];
             double2 v = hairpin_closure(tb, gt, ws.s1, i, j, cur);
-            const double2 sh = rsh(tb, ws.s1, ws.s1, i, j, iH, iS, RC);
+            const double2 sh = rshT[END_IDX(ws.s1[i], ws.s1[i + 1], ws.s1[j + 1])];
             const double G1 = v.x + sh.x - PO_TEMP_KELVIN * (v.y + sh.y);
             const double G2 = cur.x + sh.x - PO_TEMP_KELVIN * (cur.y + sh.y);
             if (G2 < G1) v = cur;
-            if (COUNT) cnt += 2;
+            if (COUNT) cnt += act ? 2 : 0;
             if (fin(v.x)) {
                 if (v.y < PO_MIN_ENTROPY_CUTOFF) v = make_double2(0.0, PO_MIN_ENTROPY);
-                ws.cell[k] = v;
+                if (act) ws.cell[k] = v;
             }
         }
         __syncwarp();
@@ -422,24 +424,29 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
     }
     __syncwarp();
     for (int i = 2; i <= len; ++i) {
-        const double2 e = end5_all<CAP>(tb, ws, lane, i, iH, iS, RC);
         const double hp = ws.end5[0][i - 1], sp = ws.end5[1][i - 1];
-        const double T1 = (hp + iH) / (sp + iS + RC);
-        const double Tv = (e.x + iH) / (e.y + iS + RC);
-        const double T2 = shfl_d(Tv, 0), T3 = shfl_d(Tv, 8), T4 = shfl_d(Tv, 16), T5 = shfl_d(Tv, 24);
-        int mx;
-        if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
-        else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
-        else if (T3 > T4 && T3 > T5) mx = 3;
-        else if (T4 > T5) mx = 4;
-        else mx = 5;
         double hn = hp, sn = sp;
-        if (mx > 1) {
-            const double eh = shfl_d(e.x, (mx - 2) * 8), es = shfl_d(e.y, (mx - 2) * 8);
-            const double G = eh - (K.temp_k * es);
-            if (G < 0.0) {
-                hn = eh;
-                sn = es;
+        // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
+        // upstream's max5() falls through to its last case, which keeps the previous value
+        const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
+        if (any) {
+            const double2 e = end5_all<CAP>(tb, ws, lane, i, iH, iS, RC);
+            const double T1 = (hp + iH) / (sp + iS + RC);
+            const double Tv = (e.x + iH) / (e.y + iS + RC);
+            const double T2 = shfl_d(Tv, 0), T3 = shfl_d(Tv, 8), T4 = shfl_d(Tv, 16), T5 = shfl_d(Tv, 24);
+            int mx;
+            if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
+            else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
+            else if (T3 > T4 && T3 > T5) mx = 3;
+            else if (T4 > T5) mx = 4;
+            else mx = 5;
+            if (mx > 1) {
+                const double eh = shfl_d(e.x, (mx - 2) * 8), es = shfl_d(e.y, (mx - 2) * 8);
+                const double G = eh - (K.temp_k * es);
+                if (G < 0.0) {
+                    hn = eh;
+                    sn = es;
+                }
             }
         }
         if (COUNT) cnt += (lane == 0) ? 4 : 0;
@@ -486,17 +493,21 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
             int myKey = KEY_NONE;
             if (q >= 5) {
                 const int ks = ws.start[q], ke = ws.start[q + 1];
-                for (int kc = ks + lane; kc < ke; kc += 32) {
+                for (int kc0 = ks; kc0 < ke; kc0 += 32) {
+                    bool act = kc0 + lane < ke;
+                    const int kc = act ? kc0 + lane : ks;
                     const int p = CODE_I(ws.code[kc]);
                     const int k = (v == 1 || v == 3) ? p - 1 : p - 2;
-                    if (k < 0) continue;
+                    act &= k >= 0;
+                    const int kk = act ? k : 0;
+                    const int bp = s[kk + 1] & 3, bp2 = s[kk + 2] & 3, bi = s[i] & 3, bim = s[i - 1] & 3;
                     double2 x = make_double2(0.0, 0.0);
-                    if (v == 2) x = tb.dangle5[(s[i] * 4 + s[k + 2]) * 4 + s[k + 1]];
-                    else if (v == 3) x = tb.dangle3[(s[i - 1] * 4 + s[i]) * 4 + s[k + 1]];
-                    else if (v == 4) x = tb.tstack2[quad(s[i - 1], s[i], s[k + 2], s[k + 1])];
+                    if (v == 2) x = tb.dangle5[(bi * 4 + bp2) * 4 + bp];
+                    else if (v == 3) x = tb.dangle3[(bim * 4 + bi) * 4 + bp];
+                    else if (v == 4) x = tb.tstack2[quad(bim, bi, bp2, bp)];
                     const double2 dv = ws.cell[kc];
                     const double aH = at_h(s[p], s[q]), aS = at_s(s[p], s[q]);
-                    const double hk = ws.end5[0][k], sk = ws.end5[1][k];
+                    const double hk = ws.end5[0][kk], sk = ws.end5[1][kk];
                     double s0, h0, s1v, h1v;
                     if (v == 1) {
                         s0 = aS + dv.y;
@@ -510,8 +521,8 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
                         h1v = hk + aH + x.x + dv.x;
                     }
                     // key: smaller k first; bit 0 = continues into the prefix structure
-                    if (eq5(si_, s0) && eq5(hi_, h0)) myKey = min(myKey, k * 2);
-                    else if (eq5(si_, s1v) && eq5(hi_, h1v)) myKey = min(myKey, k * 2 + 1);
+                    if (act && eq5(si_, s0) && eq5(hi_, h0)) myKey = min(myKey, k * 2);
+                    else if (act && eq5(si_, s1v) && eq5(hi_, h1v)) myKey = min(myKey, k * 2 + 1);
                 }
             }
             const int wKey = warp_min_int(myKey);
@@ -546,13 +557,13 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
             // bulge / interior loop
             if (j - i < 7) continue;
             const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
-            const int total = hairpin_build_queue<CAP>(ws, lane, i, j, max_loop);
+            HairpinCellCtx c;
+            const int total = hairpin_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
             if (total == 0) continue;
-            const HairpinCellCtx c = hairpin_cell_ctx<CAP>(tb, ws, i, j);
             double bT;
             int bKey;
             double2 bV;
-            hairpin_scan<CAP>(tb, ws, c, lane, total, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
+            hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
             // LAST candidate with T1 >= Tcur: largest key
             const int mxKey = warp_max_int(bKey == KEY_NONE ? -1 : bKey);
             if (mxKey < 0) continue;
@@ -566,14 +577,15 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const PoTables* gt, Hair
             if (!(eq5(cur.y, S2) && eq5(cur.x, H2))) continue;
             // first candidate (upstream order) whose value reproduces the cell
             int myKey = KEY_NONE;
-            for (int t = lane; t < total; t += 32) {
-                const int kp = ws.queue[t];
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                const bool act = t < total;
+                const int kp = ws.queue[act ? t : 0];
                 int key;
-                double2 v = hairpin_loop_term<CAP>(tb, ws, c, kp, &key);
-                if (key >= myKey) continue;
+                double2 v = hairpin_loop_term<CAP>(A, ws, c, kp, &key);
                 v = hp_fix(v.x, v.y);  // traceback == 1 form: every branch reports its value
                 const double2 pv = ws.cell[kp];
-                if (eq5(cur.y, v.y + pv.y) && eq5(cur.x, v.x + pv.x)) myKey = key;
+                if (act && key < myKey && eq5(cur.y, v.y + pv.y) && eq5(cur.x, v.x + pv.x)) myKey = key;
             }
             const int wKey = warp_min_int(myKey);
             if (wKey == KEY_NONE) continue;
