@@ -46,10 +46,12 @@ __device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const Dime
 
 // Candidate predecessors of cell (ci,cj): every finite (pi,pj) with pi < ci,
 // pj < cj and 1 <= (ci-pi-1)+(cj-pj-1) <= max_loop.  Lane l owns row ci-1-l;
-// the row's candidates are one contiguous run of the row-major list.  Also
-// publishes the cell-side loop operands (ycell).  Returns the queue length.
+// the row's candidates are one contiguous run of the row-major list, described
+// by the lane's registers {incl, cnt, first} (see run_lookup).  Also publishes
+// the cell-side loop operands (ycell): every lane stores the same four values,
+// so each lane later reads what it wrote itself and no barrier is needed.
 template <int CAP>
-__device__ __forceinline__ int dimer_build_queue(const SmemTables& tb, DimerWs<CAP>& ws, int lane, int ci, int cj,
+__device__ __forceinline__ Runs dimer_build_runs(const SmemTables& tb, DimerWs<CAP>& ws, int lane, int ci, int cj,
                                                  int max_loop, DimerCellCtx* ctx) {
     const int l1 = lane, r = ci - 1 - lane;
     const bool have = (r >= 1) & (l1 <= max_loop);
@@ -57,35 +59,30 @@ __device__ __forceinline__ int dimer_build_queue(const SmemTables& tb, DimerWs<C
     const int hi_col = (l1 == 0) ? cj - 2 : cj - 1;       // l1 + l2 >= 1
     const int lo_col = max(1, cj - 1 - (max_loop - l1));  // l1 + l2 <= max_loop
     const unsigned long long rm = ws.mask[3 - ws.s1[rr]];
-    const int cnt = have ? __popcll(rm & bit_range(lo_col - 1, hi_col - 1)) : 0;
-    const int first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
-    const int incl = warp_scan_incl(cnt, lane);
-    const int total = __shfl_sync(FULL, incl, 31);
-    const int mx = __reduce_max_sync(FULL, cnt);
-    const int off = incl - cnt;
-    for (int q = 0; q < mx; ++q)
-        if (q < cnt) ws.queue[off + q] = (uint16_t)(first + q);
+    Runs R;
+    R.cnt = have ? __popcll(rm & bit_range(lo_col - 1, hi_col - 1)) : 0;
+    R.first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
+    R.incl = warp_scan_incl(R.cnt, lane);
+    R.total = __shfl_sync(FULL, R.incl, 31);
     const int cb = ws.s1[ci], c2 = ws.s2[cj];
-    if (lane < 4) {
-        const int q = quad(c2, ws.s2[cj - 1], cb, ws.s1[ci - 1]);
-        double2 y = make_double2(0.0, 0.0);
-        if (lane == 0) y = tb.tstack[q];
-        if (lane == 1) y = make_double2(at_h(cb, c2), at_s(cb, c2));
-        if (lane == 3) y = tb.stackint2[q];
-        ws.ycell[lane] = y;
-    }
+    const int q = quad(c2, ws.s2[cj - 1], cb, ws.s1[ci - 1]);
+    const bool cAT = (cb == 0) | (cb == 3);
+    ws.ycell[0] = tb.tstack[q];
+    ws.ycell[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
+    ws.ycell[2] = make_double2(0.0, 0.0);
+    ws.ycell[3] = tb.stackint2[q];
     ctx->ci = ci;
     ctx->cj = cj;
     ctx->b1q = cb * 16 + c2;
-    __syncwarp();
-    return total;
+    return R;
 }
 
 // Forward scan of the queue: every lane keeps its best (largest T, earliest key).
 template <int CAP>
 __device__ __forceinline__ void dimer_scan(const TabAddr& A, const DimerWs<CAP>& ws, const DimerCellCtx& c, int lane,
-                                           int total, double iH, double iS, double RC, int mode, double* bT, int* bKey,
-                                           double2* bV) {
+                                           const Runs& R, double iH, double iS, double RC, int mode, double* bT,
+                                           int* bKey, double2* bV) {
+    const int total = R.total;
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 bestV = make_double2(PO_INF, -1.0);
@@ -93,7 +90,7 @@ __device__ __forceinline__ void dimer_scan(const TabAddr& A, const DimerWs<CAP>&
         const int t = t0 + lane;
         bool act = t < total;
         int key;
-        const double2 v = dimer_loop_value<CAP>(A, ws, c, ws.queue[act ? t : 0], &key);
+        const double2 v = dimer_loop_value<CAP>(A, ws, c, run_lookup(R.incl, R.cnt, R.first, act ? t : 0), &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
         if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double T1 = (v.x + iH) / ((v.y + iS) + RC);
@@ -238,15 +235,15 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             const int j = CODE_J(ws.code[k]);
             if (j == 1) continue;
             DimerCellCtx c;
-            const int total = dimer_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
-            if (COUNT) cnt += (lane == 0) ? total : 0;
-            if (total == 0) continue;
+            const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
+            if (COUNT) cnt += (lane == 0) ? R.total : 0;
+            if (R.total == 0) continue;
             const double2 cur = ws.cell[k];
             const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
             double bT, wT = -PO_INF;
             int bKey, wKey = KEY_NONE;
             double2 bV;
-            dimer_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
+            dimer_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
             int src = warp_argmax(bT, bKey, &wT, &wKey);
             if (src >= 0 && wKey == KEY_STAR) {
                 // The 1x1 loop is the arg-max.  Upstream accepts it only if it beats the
@@ -255,11 +252,11 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                 double pT, qT = -PO_INF;
                 int pKey, qKey = KEY_NONE;
                 double2 pV;
-                dimer_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
+                dimer_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
                 const int psrc = warp_argmax(pT, pKey, &qT, &qKey);
                 const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
                 if (!((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm)) {
-                    dimer_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_NO_STAR, &bT, &bKey, &bV);
+                    dimer_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_NO_STAR, &bT, &bKey, &bV);
                     src = warp_argmax(bT, bKey, &wT, &wKey);
                 }
             }
@@ -269,9 +266,8 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                     S = PO_MIN_ENTROPY;
                     H = 0.0;
                 }
-                if (fin(H) && lane == 0) ws.cell[k] = make_double2(H, S);
+                if (fin(H)) ws.cell[k] = make_double2(H, S);  // every lane stores the same value: no barrier
             }
-            __syncwarp();
         }
     }
 
@@ -340,20 +336,19 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         // loops: first candidate in upstream order whose value reproduces the cell
         const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
         DimerCellCtx c;
-        const int total = dimer_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
+        const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
         int myKey = KEY_NONE;
-        for (int t0 = 0; t0 < total; t0 += 32) {
+        for (int t0 = 0; t0 < R.total; t0 += 32) {
             const int t = t0 + lane;
-            const bool act = t < total;
+            const bool act = t < R.total;
             int key;
-            const double2 v = dimer_loop_value<CAP>(A, ws, c, ws.queue[act ? t : 0], &key);
+            const double2 v = dimer_loop_value<CAP>(A, ws, c, run_lookup(R.incl, R.cnt, R.first, act ? t : 0), &key);
             const double T1 = (v.x + iH) / ((v.y + iS) + RC);
             // traceback mode of the 1x1 branch reports its value only when T1 >= T2
             const bool ok = act & (key < myKey) & ((key != KEY_STAR) | (T1 >= Tcur));
             if (ok && eq5(cur.y, v.y) && eq5(cur.x, v.x)) myKey = key;
         }
         const int wKey = warp_min_int(myKey);
-        __syncwarp();
         if (wKey == KEY_NONE) break;  // guard: upstream would spin here (unreachable for <= 60 nt)
         const int sum = wKey >> 6, l1 = wKey & 63;
         i = i - l1 - 1;

@@ -115,10 +115,11 @@ __device__ __forceinline__ bool hp_finite(const HairpinWs<CAP>& ws, int i, int j
 
 // Candidates enclosed by (i,j): every finite (ii,jj) with i < ii, jj < j and
 // 1 <= (ii-i-1)+(j-jj-1) <= max_loop.  Lane l owns column j-1-l; the column's
-// candidates are one contiguous run of the list (rows descending).  Also
-// publishes the closing-pair loop operands (ycell).
+// candidates are one contiguous run of the list (rows descending), described by
+// the lane's registers (see run_lookup).  Also publishes the closing-pair loop
+// operands (ycell), stored identically by every lane (no barrier needed).
 template <int CAP>
-__device__ __forceinline__ int hairpin_build_queue(const SmemTables& tb, HairpinWs<CAP>& ws, int lane, int i, int j,
+__device__ __forceinline__ Runs hairpin_build_runs(const SmemTables& tb, HairpinWs<CAP>& ws, int lane, int i, int j,
                                                    int max_loop, HairpinCellCtx* ctx) {
     const int l2 = lane, jj = j - 1 - lane;
     const bool have = (jj >= 5) & (l2 <= max_loop);
@@ -126,28 +127,22 @@ __device__ __forceinline__ int hairpin_build_queue(const SmemTables& tb, Hairpin
     const int lo_row = (l2 == 0) ? i + 2 : i + 1;            // l1 + l2 >= 1
     const int hi_row = min(jc - 4, i + 1 + (max_loop - l2));  // l1 + l2 <= max_loop
     const unsigned long long cm = HP_COLMASK(ws, jc);
-    const int cnt = have ? __popcll(cm & bit_range(lo_row - 1, hi_row - 1)) : 0;
-    const int first = ws.start[jc] + __popcll(hi_row >= 0 ? (cm >> min(hi_row, 63)) : cm);
-    const int incl = warp_scan_incl(cnt, lane);
-    const int total = __shfl_sync(FULL, incl, 31);
-    const int mx = __reduce_max_sync(FULL, cnt);
-    const int off = incl - cnt;
-    for (int q = 0; q < mx; ++q)
-        if (q < cnt) ws.queue[off + q] = (uint16_t)(first + q);
+    Runs R;
+    R.cnt = have ? __popcll(cm & bit_range(lo_row - 1, hi_row - 1)) : 0;
+    R.first = ws.start[jc] + __popcll(cm >> min(max(hi_row, 0), 63));
+    R.incl = warp_scan_incl(R.cnt, lane);
+    R.total = __shfl_sync(FULL, R.incl, 31);
     const int bi = ws.s1[i], bj = ws.s1[j];
-    if (lane < 4) {
-        const int q = quad(bi, ws.s1[i + 1] & 3, bj, ws.s1[j - 1] & 3);
-        double2 y = make_double2(0.0, 0.0);
-        if (lane == 0) y = tb.tstack[q];
-        if (lane == 1) y = make_double2(at_h(bi, bj), at_s(bi, bj));
-        if (lane == 3) y = tb.stackint2[q];
-        ws.ycell[lane] = y;
-    }
+    const int q = quad(bi, ws.s1[i + 1] & 3, bj, ws.s1[j - 1] & 3);
+    const bool cAT = (bi == 0) | (bi == 3);
+    ws.ycell[0] = tb.tstack[q];
+    ws.ycell[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
+    ws.ycell[2] = make_double2(0.0, 0.0);
+    ws.ycell[3] = tb.stackint2[q];
     ctx->i = i;
     ctx->j = j;
     ctx->b1q = bi * 64 + bj * 4;
-    __syncwarp();
-    return total;
+    return R;
 }
 
 // Scan of the queue.  SCAN_LAST_GE selects the LAST candidate (largest key)
@@ -155,15 +150,16 @@ __device__ __forceinline__ int hairpin_build_queue(const SmemTables& tb, Hairpin
 // output argument.
 template <int CAP>
 __device__ __forceinline__ void hairpin_scan(const TabAddr& A, const HairpinWs<CAP>& ws, const HairpinCellCtx& c,
-                                             int lane, int total, double iH, double iS, double RC, int mode,
+                                             int lane, const Runs& R, double iH, double iS, double RC, int mode,
                                              double Tcur, double* bT, int* bKey, double2* bV) {
+    const int total = R.total;
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 bestV = make_double2(PO_INF, -1.0);
     for (int t0 = 0; t0 < total; t0 += 32) {
         const int t = t0 + lane;
         bool act = t < total;
-        const int kp = ws.queue[act ? t : 0];
+        const int kp = run_lookup(R.incl, R.cnt, R.first, act ? t : 0);
         int key;
         double2 v = hairpin_loop_term<CAP>(A, ws, c, kp, &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
@@ -363,25 +359,25 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const int i = CODE_I(ws.code[k]);
             if (j - i < 7) continue;  // no room for an enclosed pair plus a loop
             HairpinCellCtx c;
-            const int total = hairpin_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
-            if (COUNT) cnt += (lane == 0) ? total : 0;
-            if (total == 0) continue;
+            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
+            if (COUNT) cnt += (lane == 0) ? R.total : 0;
+            if (R.total == 0) continue;
             const double2 cur = ws.cell[k];
             const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
             double bT, wT = -PO_INF;
             int bKey, wKey = KEY_NONE;
             double2 bV;
-            hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
+            hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
             int src = warp_argmax(bT, bKey, &wT, &wKey);
             if (src >= 0 && wKey == KEY_STAR) {
                 double pT, qT = -PO_INF;
                 int pKey, qKey = KEY_NONE;
                 double2 pV;
-                hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey, &pV);
+                hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey, &pV);
                 const int psrc = warp_argmax(pT, pKey, &qT, &qKey);
                 const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
                 if (!((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm)) {
-                    hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_NO_STAR, Tcur, &bT, &bKey, &bV);
+                    hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_NO_STAR, Tcur, &bT, &bKey, &bV);
                     src = warp_argmax(bT, bKey, &wT, &wKey);
                 }
             }
@@ -392,10 +388,9 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
                         S = PO_MIN_ENTROPY;
                         H = 0.0;
                     }
-                    if (lane == 0) ws.cell[k] = make_double2(H, S);
+                    ws.cell[k] = make_double2(H, S);  // every lane stores the same value: no barrier
                 }
             }
-            __syncwarp();
         }
         // phase C: calc_hairpin, keep the lower dG of {loop closure, current value}
         for (int k0 = cs; k0 < ce; k0 += 32) {
@@ -558,12 +553,12 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             if (j - i < 7) continue;
             const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
             HairpinCellCtx c;
-            const int total = hairpin_build_queue<CAP>(tb, ws, lane, i, j, max_loop, &c);
-            if (total == 0) continue;
+            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
+            if (R.total == 0) continue;
             double bT;
             int bKey;
             double2 bV;
-            hairpin_scan<CAP>(A, ws, c, lane, total, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
+            hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
             // LAST candidate with T1 >= Tcur: largest key
             const int mxKey = warp_max_int(bKey == KEY_NONE ? -1 : bKey);
             if (mxKey < 0) continue;
@@ -577,10 +572,10 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             if (!(eq5(cur.y, S2) && eq5(cur.x, H2))) continue;
             // first candidate (upstream order) whose value reproduces the cell
             int myKey = KEY_NONE;
-            for (int t0 = 0; t0 < total; t0 += 32) {
+            for (int t0 = 0; t0 < R.total; t0 += 32) {
                 const int t = t0 + lane;
-                const bool act = t < total;
-                const int kp = ws.queue[act ? t : 0];
+                const bool act = t < R.total;
+                const int kp = run_lookup(R.incl, R.cnt, R.first, act ? t : 0);
                 int key;
                 double2 v = hairpin_loop_term<CAP>(A, ws, c, kp, &key);
                 v = hp_fix(v.x, v.y);  // traceback == 1 form: every branch reports its value
