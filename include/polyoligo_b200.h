@@ -152,6 +152,79 @@ int po_score_pairs_batch_dev(po_ctx *ctx, const void *d_a, const void *d_b, int6
 /* Blocks until everything enqueued on `stream` (NULL = context stream) is done. */
 int po_sync(po_ctx *ctx, void *stream);
 
+/* ---- KASP candidate enumeration ------------------------- */
+/* One marker: the homolog-mapped template around it (hroi.seq, reference
+ * src/polyoligo/_lib_kasp.py:296, OUTER_LEN = 500 nt) and the marker alleles. */
+typedef struct {
+    uint32_t tmpl[32];     /* 2-bit template, up to 512 nt, base k at bits 2k..2k+1 of word k/16 */
+    uint32_t nmask[16];    /* bit k set: template position k is not A/C/G/T               */
+    uint32_t alt[2];       /* ALT allele, 2-bit, up to 32 nt                               */
+    uint32_t alt_nmask;
+    int32_t tmpl_len;
+    int32_t marker_pos;    /* hroi.marker.pos1 - hroi.start        (_lib_kasp.py:297)      */
+    int32_t marker_pos_rc; /* hroi.stop - hroi.marker.pos1 + 1     (_lib_kasp.py:298)      */
+    int32_t ref_len;       /* len(hroi.marker.ref)                                         */
+    int32_t alt_len;       /* len(hroi.marker.alt)                                         */
+    int32_t reserved[8];
+} po_kasp_marker; /* 256 bytes */
+
+/* get_marker_primers (reference src/polyoligo/_lib_kasp.py:295-359), enumeration
+ * only: for marker m, padding p in [min_size, max_size] and direction d (0 = F,
+ * 1 = R), slot = (p - min_size) * 2 + d holds the REF primer (ref_out) and its
+ * ALT twin (alt_out) at index m * slots + slot, slots = 2 * (max_size - min_size
+ * + 1), in the reference's visiting order.  Validity (the reference keeps a
+ * slot iff both primers pass Primer.is_valid) comes from po_oligo_props_batch. */
+int po_kasp_enumerate_batch(po_ctx *ctx, const po_kasp_marker *markers, int64_t n, int min_size,
+                            int max_size, po_oligo *ref_out, po_oligo *alt_out);
+
+/* ---- heterodimer predicate, goodness score, per-marker top-n (rows a8, a9) --- */
+enum { PO_ASSAY_PCR = 0 /* also CAPS */, PO_ASSAY_KASP = 1, PO_ASSAY_HRM = 2 };
+
+/* qcode letters of scoring.py as bits, plus the KASP dimer flags */
+#define PO_Q_t 0x001
+#define PO_Q_O 0x002
+#define PO_Q_d 0x004
+#define PO_Q_m 0x008
+#define PO_Q_M 0x010
+#define PO_Q_i 0x020
+#define PO_Q_I 0x040
+#define PO_Q_h 0x080
+#define PO_Q_H 0x100
+#define PO_Q_REF_DIMER 0x1000
+#define PO_Q_ALT_DIMER 0x2000
+
+typedef struct {
+    int32_t assay;            /* PO_ASSAY_*                                              */
+    int32_t top_n;            /* n of PCR.prune(n)                                       */
+    int64_t n_pairs;
+    int64_t n_markers;
+    const po_oligo *f, *r;    /* forward / reverse primer of every pair, 5'->3'          */
+    const po_oligo *a;        /* KASP: ALT allele primer; NULL otherwise                 */
+    const uint8_t *dir;       /* KASP: 0 = marker primer is F, 1 = it is R (pp.dir)      */
+    const int64_t *seg;       /* n_markers + 1 offsets: pairs of marker m, in pps order  */
+    const int32_t *n_offtargets; /* len(pp.offtargets) (BLAST stays external glue)       */
+    const double *max_aaf;    /* n_pairs x 3: primers F, R, A (A ignored unless KASP)    */
+    const int32_t *max_indel; /* pp.max_indel_size                                        */
+    const double *hrm_delta;  /* pp.hrm["delta"]; HRM only, else NULL                     */
+    po_oligo reporters[2];    /* KASP reporter dyes (cli_kasp.py --dye1 / --dye2)        */
+    double tm_delta;
+} po_rank_in;
+
+typedef struct {
+    int32_t *goodness;        /* n_pairs                                                 */
+    int32_t *qbits;           /* n_pairs: PO_Q_* bits                                    */
+    double *tm;               /* n_pairs x 3: calcTm of F, R, A                          */
+    double *het_tm;           /* n_pairs x 2: heterodimer Tm (KASP: ref pair, alt pair)  */
+    int64_t *sel;             /* n_markers x top_n: pair indices in report order, -1 pad */
+    int32_t *n_sel;           /* n_markers                                               */
+} po_rank_out;
+
+/* PrimerPair.check_heterodimerization (reference lib_primer3.py:147-164; KASP
+ * override _lib_kasp.py:89-117 after add_reporter_dyes :75-86) + PCR.classify
+ * (scoring.py:4-151 via lib_primer3.py:425-431) + PCR.prune (lib_primer3.py:
+ * 433-463, _lib_kasp.py:278-291) for all markers of a batch. */
+int po_rank_pairs_batch(po_ctx *ctx, const po_rank_in *in, const po_rank_out *out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context has launched since po_init. */
 int64_t po_launch_count(const po_ctx *ctx);

@@ -21,7 +21,29 @@ THAL_OUT_DTYPE = np.dtype([("tm", "<f8"), ("dg", "<f8"), ("dh", "<f8"), ("ds", "
                            ("flags", "<i4"), ("align_end_1", "<i2"), ("align_end_2", "<i2")])
 PROPS_DTYPE = np.dtype([("tm", "<f8"), ("hairpin_tm", "<f8"), ("homodimer_tm", "<f8"),
                         ("gc_content", "<f8"), ("length", "<i4"), ("flags", "<i4")])
+KASP_MARKER_DTYPE = np.dtype([("tmpl", "<u4", (32,)), ("nmask", "<u4", (16,)), ("alt", "<u4", (2,)),
+                              ("alt_nmask", "<u4"), ("tmpl_len", "<i4"), ("marker_pos", "<i4"),
+                              ("marker_pos_rc", "<i4"), ("ref_len", "<i4"), ("alt_len", "<i4"),
+                              ("reserved", "<i4", (8,))])
 assert OLIGO_DTYPE.itemsize == 16 and THAL_OUT_DTYPE.itemsize == 40 and PROPS_DTYPE.itemsize == 40
+assert KASP_MARKER_DTYPE.itemsize == 256
+
+ASSAY_PCR, ASSAY_KASP, ASSAY_HRM = 0, 1, 2
+Q_BITS = {"t": 0x001, "O": 0x002, "d": 0x004, "m": 0x008, "M": 0x010, "i": 0x020, "I": 0x040, "h": 0x080,
+          "H": 0x100}
+Q_REF_DIMER, Q_ALT_DIMER = 0x1000, 0x2000
+
+
+class RankIn(C.Structure):
+    _fields_ = [("assay", C.c_int32), ("top_n", C.c_int32), ("n_pairs", C.c_int64), ("n_markers", C.c_int64),
+                ("f", C.c_void_p), ("r", C.c_void_p), ("a", C.c_void_p), ("dir", C.c_void_p), ("seg", C.c_void_p),
+                ("n_offtargets", C.c_void_p), ("max_aaf", C.c_void_p), ("max_indel", C.c_void_p),
+                ("hrm_delta", C.c_void_p), ("reporters", C.c_uint32 * 8), ("tm_delta", C.c_double)]
+
+
+class RankOut(C.Structure):
+    _fields_ = [("goodness", C.c_void_p), ("qbits", C.c_void_p), ("tm", C.c_void_p), ("het_tm", C.c_void_p),
+                ("sel", C.c_void_p), ("n_sel", C.c_void_p)]
 
 
 class ValidParams(C.Structure):
@@ -50,6 +72,9 @@ EXPORTS = {
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "po_score_pairs_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "po_kasp_enumerate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p]),
+    "po_rank_pairs_batch": (C.c_int, [C.c_void_p, C.POINTER(RankIn), C.POINTER(RankOut)]),
     "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "po_launch_count": (C.c_int64, [C.c_void_p]),
     "po_thal_count_relaxations": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
@@ -223,3 +248,58 @@ class Context:
         v = C.c_double()
         self._check(load().po_measure_fp64_peak(self._h, C.byref(v)), "po_measure_fp64_peak")
         return v.value
+
+
+    # ---- KASP enumeration and pair ranking ---------------------------------------
+    def kasp_enumerate(self, markers, min_size, max_size):
+        """markers: KASP_MARKER_DTYPE array -> (ref, alt) oligo arrays of shape (n, slots)."""
+        markers = np.ascontiguousarray(markers, dtype=KASP_MARKER_DTYPE)
+        n = len(markers)
+        slots = 2 * (max_size - min_size + 1)
+        ref = np.zeros((n, slots), dtype=OLIGO_DTYPE)
+        alt = np.zeros((n, slots), dtype=OLIGO_DTYPE)
+        self._check(load().po_kasp_enumerate_batch(self._h, markers.ctypes.data, n, min_size, max_size,
+                                                   ref.ctypes.data, alt.ctypes.data), "po_kasp_enumerate_batch")
+        return ref, alt
+
+    def rank_pairs(self, assay, f, r, seg, n_offtargets, max_aaf, max_indel, tm_delta, top_n, a=None, direction=None,
+                   hrm_delta=None, reporters=None):
+        """Heterodimer predicate + goodness + per-marker top-n for a batch of markers.
+
+        f, r (, a): OLIGO_DTYPE arrays, one entry per candidate pair; seg: n_markers+1 offsets."""
+        f = np.ascontiguousarray(f, dtype=OLIGO_DTYPE)
+        r = np.ascontiguousarray(r, dtype=OLIGO_DTYPE)
+        n = len(f)
+        seg = np.ascontiguousarray(seg, dtype=np.int64)
+        nm = len(seg) - 1
+        keep = [f, r, seg]
+        arg = RankIn()
+        arg.assay, arg.top_n, arg.n_pairs, arg.n_markers = assay, top_n, n, nm
+        arg.f, arg.r, arg.seg = f.ctypes.data, r.ctypes.data, seg.ctypes.data
+
+        def put(name, arr, dtype, shape=None):
+            if arr is None:
+                return None
+            arr = np.ascontiguousarray(arr, dtype=dtype)
+            if shape is not None:
+                arr = arr.reshape(shape)
+            keep.append(arr)
+            setattr(arg, name, arr.ctypes.data)
+            return arr
+        put("a", a, OLIGO_DTYPE)
+        put("dir", direction, np.uint8)
+        put("n_offtargets", n_offtargets, np.int32)
+        put("max_aaf", max_aaf, np.float64, (n, 3))
+        put("max_indel", max_indel, np.int32)
+        put("hrm_delta", hrm_delta, np.float64)
+        if reporters is not None:
+            rep = pack(list(reporters))
+            for k in range(8):
+                arg.reporters[k] = int(rep["w"].reshape(-1)[k])
+        arg.tm_delta = float(tm_delta)
+        res = {"goodness": np.zeros(n, dtype=np.int32), "qbits": np.zeros(n, dtype=np.int32),
+               "tm": np.zeros((n, 3)), "het_tm": np.zeros((n, 2)),
+               "sel": np.full((nm, top_n), -1, dtype=np.int64), "n_sel": np.zeros(nm, dtype=np.int32)}
+        out = RankOut(*[res[k].ctypes.data for k in ("goodness", "qbits", "tm", "het_tm", "sel", "n_sel")])
+        self._check(load().po_rank_pairs_batch(self._h, C.byref(arg), C.byref(out)), "po_rank_pairs_batch")
+        return res

@@ -8,11 +8,13 @@
 #include <mutex>
 #include <string>
 #include <type_traits>
+#include <vector>
 
 #include "po_common.h"
 #include "po_thal.cuh"
 #include "po_thal_dimer.cuh"
 #include "po_thal_hairpin.cuh"
+#include "po_pipeline.cuh"
 
 // ============================================================================
 // kernels
@@ -184,6 +186,7 @@ struct po_ctx {
     int64_t launches = 0;
     // grow-only device scratch
     DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow;
+    DevBuf scratch[12];
     unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
     // pinned staging for the host entry points
     DevBuf h_in, h_out;
@@ -274,6 +277,8 @@ extern "C" void po_destroy(po_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->a, &ctx->b, &ctx->out, &ctx->out2, &ctx->out3, &ctx->tmv, &ctx->gcv, &ctx->props, &ctx->overflow};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
+    for (DevBuf& sb : ctx->scratch)
+        if (sb.p) cudaFree(sb.p);
     if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
@@ -607,5 +612,182 @@ extern "C" int po_measure_fp64_peak(po_ctx* ctx, double* tflops) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *tflops = best;
+    return PO_OK;
+}
+
+// ============================================================================
+// KASP enumeration and pair ranking
+// ============================================================================
+extern "C" int po_kasp_enumerate_batch(po_ctx* ctx, const po_kasp_marker* markers, int64_t n, int min_size,
+                                       int max_size, po_oligo* ref_out, po_oligo* alt_out) {
+    if (!ctx || !markers || !ref_out || !alt_out || n < 0) return PO_E_INVALID;
+    if (min_size < 1 || max_size < min_size || max_size > PO_MAX_OLIGO_LEN) {
+        ctx->err = "po_kasp_enumerate_batch: need 1 <= min_size <= max_size <= 60";
+        return PO_E_INVALID;
+    }
+    if (n == 0) return PO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int slots = 2 * (max_size - min_size + 1);
+    const size_t total = (size_t)n * slots;
+    int rc;
+    if ((rc = ensure(ctx, ctx->scratch[0], sizeof(po_kasp_marker) * (size_t)n))) return rc;
+    if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * total))) return rc;
+    if ((rc = ensure(ctx, ctx->b, sizeof(po_oligo) * total))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->scratch[0].p, markers, sizeof(po_kasp_marker) * (size_t)n, cudaMemcpyHostToDevice, st));
+    const int threads = 256;
+    const long long blocks = ((long long)total + threads - 1) / threads;
+    k_kasp_enumerate<<<(unsigned)blocks, threads, 0, st>>>((const po_kasp_marker*)ctx->scratch[0].p, n, min_size,
+                                                          max_size, (uint4*)ctx->a.p, (uint4*)ctx->b.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ref_out, ctx->a.p, sizeof(po_oligo) * total, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(alt_out, ctx->b.p, sizeof(po_oligo) * total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PO_OK;
+}
+
+extern "C" int po_rank_pairs_batch(po_ctx* ctx, const po_rank_in* in, const po_rank_out* out) {
+    if (!ctx || !in || !out) return PO_E_INVALID;
+    const int64_t n = in->n_pairs, nm = in->n_markers;
+    const bool kasp = in->assay == PO_ASSAY_KASP, hrm = in->assay == PO_ASSAY_HRM;
+    if (n < 0 || nm < 0 || in->top_n < 1 || !in->f || !in->r || !in->seg || !in->n_offtargets || !in->max_aaf ||
+        !in->max_indel || !out->goodness || !out->qbits || !out->sel || !out->n_sel || (kasp && (!in->a || !in->dir)) ||
+        (hrm && !in->hrm_delta) || in->assay < 0 || in->assay > 2) {
+        ctx->err = "po_rank_pairs_batch: missing or inconsistent arguments";
+        return PO_E_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int threads = 256;
+    int rc;
+    enum { S_F = 0, S_R, S_A, S_TF, S_TR, S_TA, S_MISC, S_AAF, S_SEL, S_GOOD, S_TAILA, S_TAILB };
+    DevBuf* sb = ctx->scratch;
+    const size_t nn = (size_t)(n > 0 ? n : 1);
+    if ((rc = ensure(ctx, sb[S_F], sizeof(po_oligo) * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_R], sizeof(po_oligo) * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_A], sizeof(po_oligo) * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_TF], sizeof(double) * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_TR], sizeof(double) * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_TA], sizeof(double) * nn))) return rc;
+    // misc: n_off (i32), indel (i32), hrm_delta (f64), dir/sel (i8 x 3), seg (i64 x (nm+1)), n_sel (i32 x nm)
+    const size_t off_noff = 0, off_ind = off_noff + 4 * nn, off_hd = off_ind + 4 * nn, off_sel8 = off_hd + 8 * nn,
+                 off_seg = (off_sel8 + 3 * nn + 15) / 16 * 16, off_nsel = off_seg + 8 * (size_t)(nm + 1),
+                 misc_bytes = off_nsel + 4 * (size_t)(nm > 0 ? nm : 1);
+    if ((rc = ensure(ctx, sb[S_MISC], misc_bytes))) return rc;
+    if ((rc = ensure(ctx, sb[S_AAF], sizeof(double) * 3 * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_SEL], sizeof(long long) * (size_t)(nm > 0 ? nm : 1) * in->top_n))) return rc;
+    if ((rc = ensure(ctx, sb[S_GOOD], sizeof(int32_t) * 2 * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_TAILA], sizeof(po_oligo) * nn))) return rc;
+    if ((rc = ensure(ctx, sb[S_TAILB], sizeof(po_oligo) * nn))) return rc;
+    if ((rc = ensure(ctx, ctx->out, sizeof(po_thal_out) * nn))) return rc;
+    if ((rc = ensure(ctx, ctx->out2, sizeof(po_thal_out) * nn))) return rc;
+    char* misc = (char*)sb[S_MISC].p;
+    if (n > 0) {
+        CK(cudaMemcpyAsync(sb[S_F].p, in->f, sizeof(po_oligo) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sb[S_R].p, in->r, sizeof(po_oligo) * n, cudaMemcpyHostToDevice, st));
+        if (kasp) CK(cudaMemcpyAsync(sb[S_A].p, in->a, sizeof(po_oligo) * n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(misc + off_noff, in->n_offtargets, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(misc + off_ind, in->max_indel, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        if (hrm) CK(cudaMemcpyAsync(misc + off_hd, in->hrm_delta, 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sb[S_AAF].p, in->max_aaf, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(misc + off_seg, in->seg, 8 * (size_t)(nm + 1), cudaMemcpyHostToDevice, st));
+    const uint4* dF = (const uint4*)sb[S_F].p;
+    const uint4* dR = (const uint4*)sb[S_R].p;
+    const uint4* dA = (const uint4*)sb[S_A].p;
+    const long long blocks = (n + threads - 1) / threads;
+    if (n > 0) {
+        // calcTm of the untailed primers (Primer.calc_thermals inside check_heterodimerization)
+        if ((rc = po_tm_batch_dev(ctx, dF, n, sb[S_TF].p, nullptr, st))) return rc;
+        if ((rc = po_tm_batch_dev(ctx, dR, n, sb[S_TR].p, nullptr, st))) return rc;
+        if (kasp && (rc = po_tm_batch_dev(ctx, dA, n, sb[S_TA].p, nullptr, st))) return rc;
+        const po_thal_out* het1 = (const po_thal_out*)ctx->out.p;
+        const po_thal_out* het2 = (const po_thal_out*)ctx->out2.p;
+        if (kasp) {
+            // add_reporter_dyes: dir F -> F gets dye1, A dye2, R none; dir R -> R gets dye1, A dye2, F none.
+            // heterodimers: (F', R') and, by direction, (A', R') or (F', A').
+            std::vector<int8_t> sel(3 * (size_t)n);
+            for (int64_t k = 0; k < n; ++k) {
+                const bool dirF = in->dir[k] == 0;
+                sel[k] = dirF ? 0 : -1;                  // tail of F
+                sel[(size_t)n + k] = dirF ? -1 : 0;      // tail of R
+                sel[2 * (size_t)n + k] = 1;              // tail of A
+            }
+            CK(cudaMemcpyAsync(misc + off_sel8, sel.data(), 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));  // sel is a stack-lifetime staging buffer
+            uint4 t0, t1;
+            memcpy(&t0, &in->reporters[0], 16);
+            memcpy(&t1, &in->reporters[1], 16);
+            uint4* Ft = (uint4*)sb[S_TAILA].p;
+            uint4* Rt = (uint4*)sb[S_TAILB].p;
+            uint4* At = (uint4*)ctx->a.p;
+            if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * nn))) return rc;
+            if ((rc = ensure(ctx, ctx->b, sizeof(po_oligo) * 2 * nn))) return rc;
+            At = (uint4*)ctx->a.p;
+            const int8_t* s8 = (const int8_t*)(misc + off_sel8);
+            k_concat_tail<<<(unsigned)blocks, threads, 0, st>>>(dF, s8, t0, t1, n, Ft);
+            k_concat_tail<<<(unsigned)blocks, threads, 0, st>>>(dR, s8 + n, t0, t1, n, Rt);
+            k_concat_tail<<<(unsigned)blocks, threads, 0, st>>>(dA, s8 + 2 * n, t0, t1, n, At);
+            ctx->launches += 3;
+            CK(cudaGetLastError());
+            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, Ft, Rt, n, ctx->out.p, st))) return rc;
+            // second pair: first strand A' (dir F) or F' (dir R); second strand R' (dir F) or A' (dir R)
+            std::vector<po_oligo> dummy;
+            uint4* X1 = (uint4*)ctx->b.p;
+            uint4* X2 = X1 + n;
+            k_select_pair<<<(unsigned)blocks, threads, 0, st>>>(Ft, Rt, At, s8, n, X1, X2);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, X1, X2, n, ctx->out2.p, st))) return rc;
+        } else {
+            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, dF, dR, n, ctx->out.p, st))) return rc;
+        }
+        RankArgs ra;
+        ra.assay = in->assay;
+        ra.n = n;
+        ra.tmF = (const double*)sb[S_TF].p;
+        ra.tmR = (const double*)sb[S_TR].p;
+        ra.tmA = (const double*)sb[S_TA].p;
+        ra.het1 = het1;
+        ra.het2 = het2;
+        ra.n_off = (const int32_t*)(misc + off_noff);
+        ra.aaf = (const double*)sb[S_AAF].p;
+        ra.indel = (const int32_t*)(misc + off_ind);
+        ra.hrm_delta = (const double*)(misc + off_hd);
+        ra.tm_delta = in->tm_delta;
+        ra.goodness = (int32_t*)sb[S_GOOD].p;
+        ra.qbits = ra.goodness + n;
+        k_score_pairs<<<(unsigned)blocks, threads, 0, st>>>(ra);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (nm > 0) {
+        const long long tb = (nm * 32 + threads - 1) / threads;
+        k_top_n<<<(unsigned)tb, threads, 0, st>>>((const int32_t*)sb[S_GOOD].p, (const double*)(misc + off_hd), hrm ? 1 : 0,
+                                                  (const long long*)(misc + off_seg), nm, in->top_n,
+                                                  (long long*)sb[S_SEL].p, (int32_t*)(misc + off_nsel));
+        ctx->launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out->sel, sb[S_SEL].p, sizeof(long long) * (size_t)nm * in->top_n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->n_sel, misc + off_nsel, 4 * (size_t)nm, cudaMemcpyDeviceToHost, st));
+    }
+    if (n > 0) {
+        CK(cudaMemcpyAsync(out->goodness, sb[S_GOOD].p, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out->qbits, (int32_t*)sb[S_GOOD].p + n, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+        if (out->tm) {
+            k_gather_tm<<<(unsigned)blocks, threads, 0, st>>>((const double*)sb[S_TF].p, (const double*)sb[S_TR].p,
+                                                             kasp ? (const double*)sb[S_TA].p : nullptr,
+                                                             (const po_thal_out*)ctx->out.p,
+                                                             kasp ? (const po_thal_out*)ctx->out2.p : nullptr, n,
+                                                             (double*)sb[S_AAF].p, (double*)sb[S_TAILA].p);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(out->tm, sb[S_AAF].p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+            if (out->het_tm)
+                CK(cudaMemcpyAsync(out->het_tm, sb[S_TAILA].p, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK(cudaStreamSynchronize(st));
     return PO_OK;
 }

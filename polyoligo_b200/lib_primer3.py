@@ -1,0 +1,269 @@
+"""Host-side mirror of the hot-path parts of reference src/polyoligo/lib_primer3.py.
+
+Same names, attributes and decisions as the reference's ``Primer`` /
+``PrimerPair`` / ``PCR`` (lib_primer3.py:24-97, 111-214, 217-463) and its mask
+helpers (:564-600), but every thermodynamic quantity comes from BATCHED calls
+into the CUDA library: ``calc_thermals_batch`` evaluates any number of primers
+in one go, and the per-object methods are thin wrappers over batches of one so
+existing callers keep working.  BLAST off-target search (check_offtargeting)
+and primer3's designPrimers stay the reference's external glue and are not here.
+"""
+from copy import deepcopy
+
+import numpy as np
+
+from . import _native, lib_utils, scoring
+from .thermoanalysis import get_context, gc_content
+
+PRIMER3_GLOBALS = {}     # the PRIMER_* thresholds of the assay YAML (reference data/PRIMER3_*.yaml)
+TM_DELTA = 5             # reference lib_primer3.py:21
+
+
+def set_globals(**kwargs):
+    PRIMER3_GLOBALS.update(kwargs)
+
+
+def set_tm_delta(v):
+    global TM_DELTA
+    TM_DELTA = v
+
+
+def valid_params(tm_delta=None):
+    g = PRIMER3_GLOBALS
+    return _native.ValidParams(int(g["PRIMER_MIN_SIZE"]), int(g["PRIMER_MAX_SIZE"]), float(g["PRIMER_MIN_GC"]),
+                               float(g["PRIMER_MAX_GC"]), float(g["PRIMER_MIN_TM"]), float(g["PRIMER_MAX_TM"]),
+                               float(TM_DELTA if tm_delta is None else tm_delta))
+
+
+class Primer:
+    def __init__(self, **kwargs):
+        self.id = None
+        self.start = None
+        self.stop = None
+        self.length = None
+        self.direction = None
+        self.hairpin_tm = None
+        self.homodimer_tm = None
+        self.gc_content = None
+        self.has_thermals = False       # never set True, as in the reference (lib_primer3.py:36)
+        self.tm_delta = TM_DELTA
+        self.tm = None
+        self.mutations = []
+        self.max_aaf = 0
+        self.nN = 0
+        self.sequence = None
+        self.reporter = ""
+        for k, v in kwargs.items():
+            if k in self.__dict__:
+                setattr(self, k, deepcopy(v))
+
+    def calc_thermals(self):
+        calc_thermals_batch([self])
+
+    def is_valid(self):
+        return bool(is_valid_batch([self])[0])
+
+
+def calc_thermals_batch(primers, device=None):
+    """Primer.calc_thermals (reference lib_primer3.py:56-64) for many primers at once.
+
+    Primers containing N (or longer than 60 nt) are not evaluated on the device;
+    the reference rejects them regardless of their thermodynamics (:72-74), so
+    their tm / hairpin_tm / homodimer_tm are reported as 0.0."""
+    if not primers:
+        return np.zeros(0, dtype=_native.PROPS_DTYPE)
+    seqs = [p.sequence for p in primers]
+    props = get_context(device).oligo_props_batch(_native.pack(seqs))
+    skipped = (props["flags"] & _native.ITEM_SKIPPED) != 0
+    for p, s, rec, skip in zip(primers, seqs, props, skipped):
+        p.length = len(s)
+        p.gc_content = gc_content(s)
+        p.nN = s.count("N")
+        p.tm = 0.0 if skip else float(rec["tm"])
+        p.hairpin_tm = 0.0 if skip else float(rec["hairpin_tm"])
+        p.homodimer_tm = 0.0 if skip else float(rec["homodimer_tm"])
+    return props
+
+
+def is_valid_batch(primers, device=None):
+    """Primer.is_valid (reference lib_primer3.py:66-97) for many primers: bool array."""
+    calc_thermals_batch(primers, device)
+    g = PRIMER3_GLOBALS
+    ok = np.ones(len(primers), dtype=bool)
+    for k, p in enumerate(primers):
+        if p.nN > 0:
+            ok[k] = False
+        if p.length < g["PRIMER_MIN_SIZE"] or p.length > g["PRIMER_MAX_SIZE"]:
+            ok[k] = False
+        if p.gc_content < g["PRIMER_MIN_GC"] or p.gc_content > g["PRIMER_MAX_GC"]:
+            ok[k] = False
+        if p.tm < g["PRIMER_MIN_TM"] or p.tm > g["PRIMER_MAX_TM"]:
+            ok[k] = False
+        if p.hairpin_tm >= (p.tm - p.tm_delta):
+            ok[k] = False
+        if p.homodimer_tm >= (p.tm - p.tm_delta):
+            ok[k] = False
+    return ok
+
+
+class PrimerPair:
+    def __init__(self):
+        self.tm_delta = TM_DELTA
+        self.id = None
+        self.primers = {"F": Primer(), "R": Primer()}
+        self.offtargets = []
+        self.max_indel_size = 0
+        self.chrom = None
+        self.dimer = None
+        self.goodness = None
+        self.qcode = None
+        self.hrm = None
+        self.product_size = None
+        self.penalty = None
+        self.dir = None
+
+    def check_heterodimerization(self):
+        check_heterodimerization_batch([self])
+
+    def score(self, assay_name):
+        self.goodness, self.qcode = scoring.get_score_fnc(assay_name)(self)
+
+
+def check_heterodimerization_batch(pps, device=None):
+    """PrimerPair.check_heterodimerization (reference lib_primer3.py:147-164) for many pairs."""
+    if not pps:
+        return
+    calc_thermals_batch([p for pp in pps for p in pp.primers.values()], device)
+    f = _native.pack([pp.primers["F"].sequence for pp in pps])
+    r = _native.pack([pp.primers["R"].sequence for pp in pps])
+    het = get_context(device).thal_batch(_native.THAL_ANY, f, r)
+    for pp, rec in zip(pps, het):
+        tm_ref = float(rec["tm"])
+        pp.dimer = not ((tm_ref <= (pp.primers["F"].tm - pp.tm_delta)) and
+                        (tm_ref <= (pp.primers["R"].tm - pp.tm_delta)))
+
+
+def _rank_inputs(pps, keys):
+    n = len(pps)
+    aaf = np.zeros((n, 3))
+    for k, pp in enumerate(pps):
+        for c, d in enumerate(keys):
+            aaf[k, c] = pp.primers[d].max_aaf
+    return (np.array([len(pp.offtargets) for pp in pps], dtype=np.int32), aaf,
+            np.array([pp.max_indel_size for pp in pps], dtype=np.int32))
+
+
+class PCR:
+    def __init__(self, chrom=None, primer_pairs=None, name=None, snp_id=None, pos=None, ref=None, alt=None):
+        self.chrom, self.name, self.snp_id, self.pos, self.ref, self.alt = chrom, name, snp_id, pos, ref, alt
+        self.pps = primer_pairs if primer_pairs is not None else []
+        self.pps_classified = {}
+        self.pps_pruned = {}
+
+    def check_heterodimerization(self):
+        check_heterodimerization_batch(self.pps)
+
+    def classify(self, assay_name):
+        for pp in self.pps:
+            pp.score(assay_name)
+            self.pps_classified.setdefault(pp.goodness, []).append(pp)
+
+    def prune(self, n, assay_name="generic"):
+        """Best n pairs: descending goodness, insertion order inside a class (HRM:
+        larger delta first).  reference lib_primer3.py:433-463."""
+        nprim = 0
+        for score in sorted(self.pps_classified, reverse=True):
+            group = self.pps_classified[score]
+            if assay_name == "HRM":
+                order = np.argsort(-np.array([pp.hrm["delta"] for pp in group]), kind="stable")
+                group = [group[i] for i in order]
+            self.pps_pruned[score] = group[:max(0, n - nprim)]
+            nprim += len(self.pps_pruned[score])
+        return nprim
+
+    def rank(self, n, assay_name, device=None):
+        """check_heterodimerization + classify + prune in one device pass
+        (po_rank_pairs_batch); fills the same attributes the three calls would."""
+        rank_batch([self], n, assay_name, device)
+        return sum(len(v) for v in self.pps_pruned.values())
+
+
+def rank_batch(pcrs, n, assay_name, device=None, reporters=None):
+    """Heterodimer check, goodness and top-n for MANY markers/regions in one call."""
+    kasp = assay_name == "KASP"
+    assay = {"KASP": _native.ASSAY_KASP, "HRM": _native.ASSAY_HRM}.get(assay_name, _native.ASSAY_PCR)
+    keys = ["F", "R", "A"] if kasp else ["F", "R"]
+    pps = [pp for pcr in pcrs for pp in pcr.pps]
+    seg = np.zeros(len(pcrs) + 1, dtype=np.int64)
+    np.cumsum([len(pcr.pps) for pcr in pcrs], out=seg[1:])
+    if not pps:
+        return
+    n_off, aaf, indel = _rank_inputs(pps, keys)
+    kw = {}
+    if kasp:
+        kw["a"] = _native.pack([pp.primers["A"].sequence for pp in pps])
+        kw["direction"] = np.array([0 if pp.dir == "F" else 1 for pp in pps], dtype=np.uint8)
+        kw["reporters"] = reporters
+    if assay_name == "HRM":
+        kw["hrm_delta"] = np.array([pp.hrm["delta"] for pp in pps])
+    res = get_context(device).rank_pairs(assay, _native.pack([pp.primers["F"].sequence for pp in pps]),
+                                         _native.pack([pp.primers["R"].sequence for pp in pps]), seg, n_off, aaf,
+                                         indel, pps[0].tm_delta, n, **kw)
+    for k, pp in enumerate(pps):
+        for c, d in enumerate(keys):
+            pp.primers[d].tm = float(res["tm"][k, c])
+        bits = int(res["qbits"][k])
+        if kasp:
+            pp.ref_dimer = bool(bits & _native.Q_REF_DIMER)
+            pp.alt_dimer = bool(bits & _native.Q_ALT_DIMER)
+        else:
+            pp.dimer = bool(bits & _native.Q_BITS["d"])
+        pp.goodness = int(res["goodness"][k])
+        pp.qcode = scoring.qcode_from_bits(bits)
+    for m, pcr in enumerate(pcrs):
+        pcr.pps_classified, pcr.pps_pruned = {}, {}
+        for pp in pcr.pps:
+            pcr.pps_classified.setdefault(pp.goodness, []).append(pp)
+        for idx in res["sel"][m, :res["n_sel"][m]]:
+            pp = pps[int(idx)]
+            pcr.pps_pruned.setdefault(pp.goodness, []).append(pp)
+
+
+# ---- masks ---------------------------------------------------
+def get_exclusion_zone(v, hard_exclude=None):
+    """Positions a primer may not cover -> [[start, length], ...] (reference lib_primer3.py:564-573)."""
+    idx = np.flatnonzero(~np.asarray(v, dtype=bool))
+    if hard_exclude is not None and len(hard_exclude):
+        idx = np.union1d(idx, np.asarray(hard_exclude, dtype=np.int64))
+    return lib_utils.list_2_ranges(idx)
+
+
+def include_mut_in_included_maps(hroi):
+    """Adds a '<name>_mut' twin of every inclusion map with the VCF mutation positions
+    cleared (reference lib_primer3.py:576-593)."""
+    maps = {}
+    for k, mmap in hroi.p3_sequence_included_maps.items():
+        maps[k] = np.array(mmap, dtype=bool, copy=True)
+        if hroi.vcf_hook:
+            twin = np.array(mmap, dtype=bool, copy=True)
+            pos = np.array([m.pos - hroi.start for m in hroi.mutations], dtype=np.int64)
+            twin[pos] = False
+            maps[k + "_mut"] = twin
+    hroi.p3_sequence_included_maps = maps
+
+
+def get_sequence_excluded_regions(hroi):
+    hroi.p3_sequence_excluded_regions = {k: get_exclusion_zone(m) for k, m in hroi.p3_sequence_included_maps.items()}
+
+
+def open_marker_window(hroi):
+    """The KASP step 'make sure the marker region of the primer is made available'
+    (reference _lib_kasp.py:681-684), restated literally: ``start`` is computed
+    from the GENOME coordinate hroi.start, so for any region further than
+    PRIMER_MAX_SIZE from the chromosome start the slice is [1:] and every map
+    is opened except index 0 (not 'fixed')."""
+    size = PRIMER3_GLOBALS["PRIMER_MAX_SIZE"]
+    for mmap in hroi.p3_sequence_included_maps.values():
+        start = min(1, hroi.start - size)
+        stop = max(len(mmap), hroi.start + size)
+        mmap[start:stop] = True

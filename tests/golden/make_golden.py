@@ -118,7 +118,7 @@ def golden_heterodimer(rng):
             f = rand_seq(rng, int(rng.integers(18, 26)))
             r = rand_seq(rng, int(rng.integers(18, 26)))
             if k % 7 == 0:   # force a strong dimer
-                r = lp.Seq(f[-12:]).reverse_complement() + r[12:]
+                r = lp.Seq(f[-18:]).reverse_complement() + r[18:]
             pp = lp.PrimerPair()
             pp.tm_delta = tm_delta
             pp.primers["F"].sequence = f
@@ -134,7 +134,7 @@ def golden_heterodimer(rng):
             alt = core[:-1] + rng.choice([c for c in "ACGT" if c != core[-1]])
             com = rand_seq(rng, int(rng.integers(18, 26)))
             if k % 5 == 0:
-                com = str(lp.Seq((VIC + core)[-14:]).reverse_complement()) + com[14:]
+                com = str(lp.Seq((VIC + core)[-20:]).reverse_complement()) + com[20:]
             pp = lk.PrimerPair()
             pp.tm_delta = tm_delta
             pp.dir = direction
