@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolyoligo_b200.so")
+LIB_PATH = os.environ.get("POLYOLIGO_B200_LIB", os.path.join(_HERE, "libpolyoligo_b200.so"))
 
 THAL_ANY, THAL_END1, THAL_END2, THAL_HAIRPIN = 1, 2, 3, 4
 ITEM_STRUCTURE_FOUND, ITEM_SKIPPED, ITEM_SYMMETRIC, PRIMER_VALID = 0x1, 0x2, 0x4, 0x100

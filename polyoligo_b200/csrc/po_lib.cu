@@ -44,7 +44,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
     SmemExtra* xt = reinterpret_cast<SmemExtra*>(smem + sizeof(SmemTables));
     Ws* wsAll = reinterpret_cast<Ws*>(smem + sizeof(SmemTables) + sizeof(SmemExtra));
     stage_tables(tb, gt);
-    fill_extra(xt, *tb, K);
+    fill_extra(xt, *tb, K, gt);
     const TabAddr TA = tab_addr(*tb, *xt);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Ws& ws = wsAll[warp];

@@ -52,25 +52,31 @@ __device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const Dime
 // so each lane later reads what it wrote itself and no barrier is needed.
 template <int CAP>
 __device__ __forceinline__ Runs dimer_build_runs(const SmemTables& tb, DimerWs<CAP>& ws, int lane, int ci, int cj,
-                                                 int max_loop, DimerCellCtx* ctx) {
+                                                 int max_loop, bool prune, DimerCellCtx* ctx) {
     const int l1 = lane, r = ci - 1 - lane;
     const bool have = (r >= 1) & (l1 <= max_loop);
     const int rr = have ? r : 1;
+    const int cb = ws.s1[ci], c2 = ws.s2[cj];
+    const int q = quad(c2, ws.s2[cj - 1], cb, ws.s1[ci - 1]);
+    const double2 y0 = tb.tstack[q], y3 = tb.stackint2[q];
+    // When both cell-side terms are infinite every interior / 1x1 candidate is rejected
+    // (dH = +inf never wins and never matches in the traceback): only bulges remain, i.e.
+    // row ci-1 (l1 == 0) and column cj-1 (l2 == 0).
+    const bool interior_ok = fin(y0.x) | fin(y3.x);
     const int hi_col = (l1 == 0) ? cj - 2 : cj - 1;       // l1 + l2 >= 1
-    const int lo_col = max(1, cj - 1 - (max_loop - l1));  // l1 + l2 <= max_loop
+    int lo_col = max(1, cj - 1 - (max_loop - l1));        // l1 + l2 <= max_loop
+    if (prune && !interior_ok && l1 > 0) lo_col = max(lo_col, cj - 1);
     const unsigned long long rm = ws.mask[3 - ws.s1[rr]];
     Runs R;
     R.cnt = have ? __popcll(rm & bit_range(lo_col - 1, hi_col - 1)) : 0;
     R.first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
     R.incl = warp_scan_incl(R.cnt, lane);
     R.total = __shfl_sync(FULL, R.incl, 31);
-    const int cb = ws.s1[ci], c2 = ws.s2[cj];
-    const int q = quad(c2, ws.s2[cj - 1], cb, ws.s1[ci - 1]);
     const bool cAT = (cb == 0) | (cb == 3);
-    ws.ycell[0] = tb.tstack[q];
+    ws.ycell[0] = y0;
     ws.ycell[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
     ws.ycell[2] = make_double2(0.0, 0.0);
-    ws.ycell[3] = tb.stackint2[q];
+    ws.ycell[3] = y3;
     ctx->ci = ci;
     ctx->cj = cj;
     ctx->b1q = cb * 16 + c2;
@@ -93,7 +99,7 @@ __device__ __forceinline__ void dimer_scan(const TabAddr& A, const DimerWs<CAP>&
         const double2 v = dimer_loop_value<CAP>(A, ws, c, run_lookup(R.incl, R.cnt, R.first, act ? t : 0), &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
         if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
-        const double T1 = (v.x + iH) / ((v.y + iS) + RC);
+        const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
         if (act & ((T1 > bestT) | ((T1 == bestT) & (key < bestKey)))) {
             bestT = T1;
             bestKey = key;
@@ -213,7 +219,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                     S1 = pv.y + st.y;
                     H1 = pv.x + st.x;
                 }
-                const double T1 = have ? (H1 + iH + sh.x) / (S1 + iS + RC + sh.y) : (H1 + iH) / (S1 + iS + RC);
+                const double T1 = have ? po_div(H1 + iH + sh.x, S1 + iS + RC + sh.y) : po_div(H1 + iH, S1 + iS + RC);
                 if (S1 < PO_MIN_ENTROPY_CUTOFF) {
                     S1 = PO_MIN_ENTROPY;
                     H1 = 0.0;
@@ -235,7 +241,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             const int j = CODE_J(ws.code[k]);
             if (j == 1) continue;
             DimerCellCtx c;
-            const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
+            const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, !COUNT, &c);
             if (COUNT) cnt += (lane == 0) ? R.total : 0;
             if (R.total == 0) continue;
             const double2 cur = ws.cell[k];
@@ -336,14 +342,14 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         // loops: first candidate in upstream order whose value reproduces the cell
         const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
         DimerCellCtx c;
-        const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
+        const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, true, &c);
         int myKey = KEY_NONE;
         for (int t0 = 0; t0 < R.total; t0 += 32) {
             const int t = t0 + lane;
             const bool act = t < R.total;
             int key;
             const double2 v = dimer_loop_value<CAP>(A, ws, c, run_lookup(R.incl, R.cnt, R.first, act ? t : 0), &key);
-            const double T1 = (v.x + iH) / ((v.y + iS) + RC);
+            const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
             // traceback mode of the 1x1 branch reports its value only when T1 >= T2
             const bool ok = act & (key < myKey) & ((key != KEY_STAR) | (T1 >= Tcur));
             if (ok && eq5(cur.y, v.y) && eq5(cur.x, v.x)) myKey = key;

@@ -57,8 +57,8 @@ __device__ __forceinline__ double2 bonus_lookup(const int32_t* keys, const doubl
 
 // upstream calc_hairpin() without its final dG comparison: the hairpin-loop
 // closure value of (i,j); `cur` is the current DP value of the cell.
-__device__ __forceinline__ double2 hairpin_closure(const SmemTables& tb, const PoTables* gt, const uint8_t* s, int i,
-                                                   int j, double2 cur) {
+__device__ __forceinline__ double2 hairpin_closure(const SmemTables& tb, const SmemExtra& X, const PoTables* gt,
+                                                   const uint8_t* s, int i, int j, double2 cur) {
     const int loopSize = j - i - 1;
     double H, S;
     const int li = loopSize <= 30 ? loopSize - 1 : 29;
@@ -73,19 +73,28 @@ __device__ __forceinline__ double2 hairpin_closure(const SmemTables& tb, const P
         S += at_s(s[i], s[j]);
     }
     if (loopSize == 3) {
-        if (gt->n_tri) {
+        if (X.n_tri) {
             int key = 0;
 #pragma unroll
-            for (int c = 0; c < 5; ++c) key |= s[i + c] << (2 * c);
-            const double2 b = bonus_lookup(gt->tri_key, gt->tri_val, gt->n_tri, key);
+            for (int c = 0; c < 5; ++c) key |= (s[i + c] & 3) << (2 * c);
+            double2 b = make_double2(0.0, 0.0);
+            if (X.n_tri <= 16) {  // shared-memory copy, sorted: 4-step branch-free search
+                int pos = 0;
+#pragma unroll
+                for (int st = 8; st >= 1; st >>= 1) pos += (X.tri_key[pos + st - 1] < key) ? st : 0;
+                pos = min(pos, 15);
+                if (X.tri_key[pos] == key) b = X.tri_val[pos];
+            } else {
+                b = bonus_lookup(gt->tri_key, gt->tri_val, gt->n_tri, key);
+            }
             H += b.x;
             S += b.y;
         }
     } else if (loopSize == 4) {
-        if (gt->n_tetra) {
+        if (X.n_tetra) {
             int key = 0;
 #pragma unroll
-            for (int c = 0; c < 6; ++c) key |= s[i + c] << (2 * c);
+            for (int c = 0; c < 6; ++c) key |= (s[i + c] & 3) << (2 * c);
             const double2 b = bonus_lookup(gt->tetra_key, gt->tetra_val, gt->n_tetra, key);
             H += b.x;
             S += b.y;
@@ -120,25 +129,29 @@ __device__ __forceinline__ bool hp_finite(const HairpinWs<CAP>& ws, int i, int j
 // operands (ycell), stored identically by every lane (no barrier needed).
 template <int CAP>
 __device__ __forceinline__ Runs hairpin_build_runs(const SmemTables& tb, HairpinWs<CAP>& ws, int lane, int i, int j,
-                                                   int max_loop, HairpinCellCtx* ctx) {
+                                                   int max_loop, bool prune, HairpinCellCtx* ctx) {
     const int l2 = lane, jj = j - 1 - lane;
     const bool have = (jj >= 5) & (l2 <= max_loop);
     const int jc = have ? jj : 5;
+    const int bi = ws.s1[i], bj = ws.s1[j];
+    const int q = quad(bi, ws.s1[i + 1] & 3, bj, ws.s1[j - 1] & 3);
+    const double2 y0 = tb.tstack[q], y3 = tb.stackint2[q];
+    // both closing-pair terms infinite: only bulges (l2 == 0 or l1 == 0) can be finite
+    const bool interior_ok = fin(y0.x) | fin(y3.x);
     const int lo_row = (l2 == 0) ? i + 2 : i + 1;            // l1 + l2 >= 1
-    const int hi_row = min(jc - 4, i + 1 + (max_loop - l2));  // l1 + l2 <= max_loop
+    int hi_row = min(jc - 4, i + 1 + (max_loop - l2));        // l1 + l2 <= max_loop
+    if (prune && !interior_ok && l2 > 0) hi_row = min(hi_row, i + 1);
     const unsigned long long cm = HP_COLMASK(ws, jc);
     Runs R;
     R.cnt = have ? __popcll(cm & bit_range(lo_row - 1, hi_row - 1)) : 0;
     R.first = ws.start[jc] + __popcll(cm >> min(max(hi_row, 0), 63));
     R.incl = warp_scan_incl(R.cnt, lane);
     R.total = __shfl_sync(FULL, R.incl, 31);
-    const int bi = ws.s1[i], bj = ws.s1[j];
-    const int q = quad(bi, ws.s1[i + 1] & 3, bj, ws.s1[j - 1] & 3);
     const bool cAT = (bi == 0) | (bi == 3);
-    ws.ycell[0] = tb.tstack[q];
+    ws.ycell[0] = y0;
     ws.ycell[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
     ws.ycell[2] = make_double2(0.0, 0.0);
-    ws.ycell[3] = tb.stackint2[q];
+    ws.ycell[3] = y3;
     ctx->i = i;
     ctx->j = j;
     ctx->b1q = bi * 64 + bj * 4;
@@ -168,7 +181,7 @@ __device__ __forceinline__ void hairpin_scan(const TabAddr& A, const HairpinWs<C
         v.x += pv.x;
         v.y += pv.y;
         v = hp_fix(v.x, v.y);
-        const double T1 = (v.x + iH) / ((v.y + iS) + RC);
+        const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
         bool take;
         if (mode == SCAN_LAST_GE) take = act & (T1 >= Tcur) & ((bestKey == KEY_NONE) | (key > bestKey));
         else take = act & ((T1 > bestT) | ((T1 == bestT) & (key < bestKey)));
@@ -216,7 +229,7 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
         else if (v == 4) x = tb.tstack2[quad(bim, bi, bp2, bp)];        // Htstack(i-1, k+2)
         const double2 dv = ws.cell[kc];
         const double hk = ws.end5[0][kk], sk = ws.end5[1][kk];
-        const double T1p = (hk + iH) / (sk + iS + RC);
+        const double T1p = po_div(hk + iH, sk + iS + RC);
         double H, S;
         const int pp = act ? p : 1, qq = act ? q : 1;
         const double aH = at_h(s[pp], s[qq]), aS = at_s(s[pp], s[qq]);
@@ -241,7 +254,7 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
             H = PO_INF;
             S = -1.0;
         }
-        const double T1 = (H + iH) / (S + iS + RC);
+        const double T1 = po_div(H + iH, S + iS + RC);
         // upstream keeps the first k with the strictly largest T1; -inf never wins
         if (act & (S > PO_MIN_ENTROPY_CUTOFF) & (T1 > -PO_INF) & ((T1 > bestT) | ((T1 == bestT) & (k < bestKey)))) {
             bestT = T1;
@@ -342,7 +355,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const double2 st = tb.stack[quad(ws.s1[i], ws.s1[i + 1], ws.s1[j], ws.s1[j - 1])];
             double S1 = pv.y + st.y;
             double H1 = pv.x + st.x;
-            const double T1 = (H1 + iH) / (S1 + iS + RC);
+            const double T1 = po_div(H1 + iH, S1 + iS + RC);
             if (S1 < PO_MIN_ENTROPY_CUTOFF) {
                 S1 = PO_MIN_ENTROPY;
                 H1 = 0.0;
@@ -359,7 +372,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const int i = CODE_I(ws.code[k]);
             if (j - i < 7) continue;  // no room for an enclosed pair plus a loop
             HairpinCellCtx c;
-            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
+            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, !COUNT, &c);
             if (COUNT) cnt += (lane == 0) ? R.total : 0;
             if (R.total == 0) continue;
             const double2 cur = ws.cell[k];
@@ -398,7 +411,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const int k = act ? k0 + lane : ce - 1;
             const int i = CODE_I(ws.code[k]);
             const double2 cur = ws.cell[k];
-            double2 v = hairpin_closure(tb, gt, ws.s1, i, j, cur);
+            double2 v = hairpin_closure(tb, X, gt, ws.s1, i, j, cur);
             const double2 sh = rshT[END_IDX(ws.s1[i], ws.s1[i + 1], ws.s1[j + 1])];
             const double G1 = v.x + sh.x - PO_TEMP_KELVIN * (v.y + sh.y);
             const double G2 = cur.x + sh.x - PO_TEMP_KELVIN * (cur.y + sh.y);
@@ -426,8 +439,8 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
         const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
         if (any) {
             const double2 e = end5_all<CAP>(tb, ws, lane, i, iH, iS, RC);
-            const double T1 = (hp + iH) / (sp + iS + RC);
-            const double Tv = (e.x + iH) / (e.y + iS + RC);
+            const double T1 = po_div(hp + iH, sp + iS + RC);
+            const double Tv = po_div(e.x + iH, e.y + iS + RC);
             const double T2 = shfl_d(Tv, 0), T3 = shfl_d(Tv, 8), T4 = shfl_d(Tv, 16), T5 = shfl_d(Tv, 24);
             int mx;
             if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
@@ -547,13 +560,13 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
                 }
             }
             // hairpin loop closes here
-            const double2 hv = hairpin_closure(tb, gt, ws.s1, i, j, cur);
+            const double2 hv = hairpin_closure(tb, X, gt, ws.s1, i, j, cur);
             if (eq5(cur.y, hv.y) && eq5(cur.x, hv.x)) continue;
             // bulge / interior loop
             if (j - i < 7) continue;
             const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
             HairpinCellCtx c;
-            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, &c);
+            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, true, &c);
             if (R.total == 0) continue;
             double bT;
             int bKey;
