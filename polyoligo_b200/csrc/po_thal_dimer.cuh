@@ -207,7 +207,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                 if (COUNT) cnt += act ? 1 : 0;
                 const double S0 = v.y, H0 = v.x;
                 const double2 sh = RSH_AT(i, j);
-                const double T0 = (H0 + iH + sh.x) / (S0 + iS + RC + sh.y);
+                const double T0 = po_div(H0 + iH + sh.x, S0 + iS + RC + sh.y);
                 double S1 = -1.0, H1 = PO_INF;
                 const unsigned long long pm = ROWMASK(i - 1);
                 const bool pfin = (pm >> (j - 2)) & 1ull;
@@ -245,7 +245,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             if (COUNT) cnt += (lane == 0) ? R.total : 0;
             if (R.total == 0) continue;
             const double2 cur = ws.cell[k];
-            const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
+            const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
             double bT, wT = -PO_INF;
             int bKey, wKey = KEY_NONE;
             double2 bV;
@@ -340,7 +340,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             }
         }
         // loops: first candidate in upstream order whose value reproduces the cell
-        const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
+        const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
         DimerCellCtx c;
         const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, true, &c);
         int myKey = KEY_NONE;

@@ -213,7 +213,7 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
     const int n_im = i >= 6 ? ws.start[i] - ws.start[i - 1] : 0;
     const int trips = (max(n_i, n_im) + 7) >> 3;
     const int ks = q >= 5 ? ws.start[q] : 0, ke = q >= 5 ? ws.start[q + 1] : 0;
-    const double T2 = (0 + iH) / (0 + iS + RC);
+    const double T2 = po_div(0 + iH, 0 + iS + RC);
     for (int it = 0; it < trips; ++it) {
         const int kc0 = ks + sub + 8 * it;
         bool act = kc0 < ke;
@@ -348,7 +348,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const int k = act ? k0 + lane : ce - 1;
             const int i = CODE_I(ws.code[k]);
             double S0 = PO_MIN_ENTROPY, H0 = 0.0;
-            const double T0 = (H0 + iH) / (S0 + iS + RC);
+            const double T0 = po_div(H0 + iH, S0 + iS + RC);
             const bool pfin = hp_finite<CAP>(ws, i + 1, j - 1);
             double2 pv = ws.cell[pfin ? hp_index<CAP>(ws, i + 1, j - 1) : 0];
             if (!pfin) pv = make_double2(PO_INF, -1.0);
@@ -376,7 +376,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             if (COUNT) cnt += (lane == 0) ? R.total : 0;
             if (R.total == 0) continue;
             const double2 cur = ws.cell[k];
-            const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
+            const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
             double bT, wT = -PO_INF;
             int bKey, wKey = KEY_NONE;
             double2 bV;
@@ -564,7 +564,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             if (eq5(cur.y, hv.y) && eq5(cur.x, hv.x)) continue;
             // bulge / interior loop
             if (j - i < 7) continue;
-            const double Tcur = (cur.x + iH) / ((cur.y + iS) + RC);
+            const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
             HairpinCellCtx c;
             const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, true, &c);
             if (R.total == 0) continue;
