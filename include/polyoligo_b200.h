@@ -225,6 +225,28 @@ typedef struct {
  * 433-463, _lib_kasp.py:278-291) for all markers of a batch. */
 int po_rank_pairs_batch(po_ctx *ctx, const po_rank_in *in, const po_rank_out *out);
 
+/* ---- "next" rows of SURVEY 8f ------------------------------------------------ */
+/* HRM product melting temperature: Biopython 1.76 MeltingTemp.Tm_NN(seq,
+ * strict=False) with its defaults (Allawi & SantaLucia 1997 table DNA_NN3,
+ * dnac1 = dnac2 = 25 nM, Na = 50 mM, saltcorr = 5) as called by get_tm
+ * (reference src/polyoligo/lib_markers.py:586-587) from
+ * PCRproduct.get_hrm_temps (:518-529).  Products are 40-150 nt, longer than an
+ * oligo record, so the input is ASCII: item k = bytes [offsets[k], offsets[k+1]).
+ * A sequence with a non-ACGT letter yields NaN (Biopython raises ValueError). */
+int po_tm_nn_batch(po_ctx *ctx, const char *ascii, const int64_t *offsets, int64_t n, double *tm);
+
+/* Numeric part of PrimerPair.add_mutations (reference src/polyoligo/
+ * lib_primer3.py:166-210): max alternative-allele frequency of the mutations
+ * inside every primer window [start, stop] and the largest indel inside the
+ * product window [F.start, R.stop].  Mutations and pairs are grouped per marker
+ * (mut_seg / pair_seg: n_markers + 1 offsets).  primer_start / primer_stop are
+ * n_pairs x 3 (F, R, A; A ignored when n_primers == 2). */
+int po_annotate_mutations_batch(po_ctx *ctx, const int64_t *mut_pos, const double *mut_aaf,
+                                const int32_t *mut_indel, const int64_t *mut_seg,
+                                const int64_t *pair_seg, int64_t n_markers,
+                                const int64_t *primer_start, const int64_t *primer_stop,
+                                int n_primers, double *max_aaf, int32_t *max_indel);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context has launched since po_init. */
 int64_t po_launch_count(const po_ctx *ctx);

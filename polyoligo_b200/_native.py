@@ -75,6 +75,9 @@ EXPORTS = {
     "po_kasp_enumerate_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p]),
     "po_rank_pairs_batch": (C.c_int, [C.c_void_p, C.POINTER(RankIn), C.POINTER(RankOut)]),
+    "po_tm_nn_batch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "po_annotate_mutations_batch": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p,
+                                                                               C.c_int, C.c_void_p, C.c_void_p]),
     "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "po_launch_count": (C.c_int64, [C.c_void_p]),
     "po_thal_count_relaxations": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
@@ -303,3 +306,31 @@ class Context:
         out = RankOut(*[res[k].ctypes.data for k in ("goodness", "qbits", "tm", "het_tm", "sel", "n_sel")])
         self._check(load().po_rank_pairs_batch(self._h, C.byref(arg), C.byref(out)), "po_rank_pairs_batch")
         return res
+
+    # ---- "next" rows: HRM product Tm, mutation annotation ---------------------------
+    def tm_nn_batch(self, seqs):
+        """Biopython Tm_NN (defaults) of each sequence; NaN where Biopython would raise."""
+        blob, off = _seq_blob(seqs)
+        n = len(off) - 1
+        out = np.empty(n, dtype=np.float64)
+        self._check(load().po_tm_nn_batch(self._h, blob.tobytes() if blob.size else b"", off.ctypes.data, n,
+                                          out.ctypes.data), "po_tm_nn_batch")
+        return out
+
+    def annotate_mutations(self, mut_pos, mut_aaf, mut_indel, mut_seg, pair_seg, primer_start, primer_stop,
+                           n_primers):
+        mut_pos = np.ascontiguousarray(mut_pos, dtype=np.int64)
+        mut_aaf = np.ascontiguousarray(mut_aaf, dtype=np.float64)
+        mut_indel = np.ascontiguousarray(mut_indel, dtype=np.int32)
+        mut_seg = np.ascontiguousarray(mut_seg, dtype=np.int64)
+        pair_seg = np.ascontiguousarray(pair_seg, dtype=np.int64)
+        n_pairs = int(pair_seg[-1]) if len(pair_seg) else 0
+        ps = np.ascontiguousarray(primer_start, dtype=np.int64).reshape(n_pairs, 3)
+        pe = np.ascontiguousarray(primer_stop, dtype=np.int64).reshape(n_pairs, 3)
+        aaf = np.zeros((n_pairs, 3))
+        indel = np.zeros(n_pairs, dtype=np.int32)
+        self._check(load().po_annotate_mutations_batch(
+            self._h, mut_pos.ctypes.data, mut_aaf.ctypes.data, mut_indel.ctypes.data, mut_seg.ctypes.data,
+            pair_seg.ctypes.data, len(mut_seg) - 1, ps.ctypes.data, pe.ctypes.data, n_primers, aaf.ctypes.data,
+            indel.ctypes.data), "po_annotate_mutations_batch")
+        return aaf, indel

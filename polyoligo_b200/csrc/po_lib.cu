@@ -791,3 +791,80 @@ extern "C" int po_rank_pairs_batch(po_ctx* ctx, const po_rank_in* in, const po_r
     CK(cudaStreamSynchronize(st));
     return PO_OK;
 }
+
+// ============================================================================
+// "next" rows: HRM product Tm and mutation annotation
+// ============================================================================
+extern "C" int po_tm_nn_batch(po_ctx* ctx, const char* ascii, const int64_t* offsets, int64_t n, double* tm) {
+    if (!ctx || !ascii || !offsets || !tm || n < 0) return PO_E_INVALID;
+    if (n == 0) return PO_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)offsets[n];
+    int rc;
+    if ((rc = ensure(ctx, ctx->scratch[0], bytes + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->scratch[1], sizeof(int64_t) * (size_t)(n + 1)))) return rc;
+    if ((rc = ensure(ctx, ctx->tmv, sizeof(double) * (size_t)n))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->scratch[0].p, ascii, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->scratch[1].p, offsets, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    TmNNConsts K;
+    K.log_mon = log((50 + 0 + 0 / 2.0) * 1e-3);        // salt_correction(Na=50, K=0, Tris=0), method 5
+    K.r_log_k = 1.987 * (log((25 - (25 / 2.0)) * 1e-9));  // dnac1 = dnac2 = 25 nM, selfcomp False
+    const int threads = 128;
+    const long long blocks = (n + threads - 1) / threads;
+    k_tm_nn<<<(unsigned)blocks, threads, 0, st>>>((const char*)ctx->scratch[0].p, (const long long*)ctx->scratch[1].p, n,
+                                                 K, (double*)ctx->tmv.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(tm, ctx->tmv.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PO_OK;
+}
+
+extern "C" int po_annotate_mutations_batch(po_ctx* ctx, const int64_t* mut_pos, const double* mut_aaf,
+                                           const int32_t* mut_indel, const int64_t* mut_seg, const int64_t* pair_seg,
+                                           int64_t n_markers, const int64_t* primer_start, const int64_t* primer_stop,
+                                           int n_primers, double* max_aaf, int32_t* max_indel) {
+    if (!ctx || !mut_seg || !pair_seg || !primer_start || !primer_stop || !max_aaf || !max_indel || n_markers < 0 ||
+        (n_primers != 2 && n_primers != 3))
+        return PO_E_INVALID;
+    if (n_markers == 0) return PO_OK;
+    const int64_t n_mut = mut_seg[n_markers], n_pairs = pair_seg[n_markers];
+    if (n_pairs == 0) return PO_OK;
+    if (n_mut > 0 && (!mut_pos || !mut_aaf || !mut_indel)) return PO_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    DevBuf* sb = ctx->scratch;
+    const size_t nm1 = (size_t)(n_markers + 1), nmu = (size_t)(n_mut > 0 ? n_mut : 1), np_ = (size_t)n_pairs;
+    if ((rc = ensure(ctx, sb[0], 8 * nmu))) return rc;
+    if ((rc = ensure(ctx, sb[1], 8 * nmu))) return rc;
+    if ((rc = ensure(ctx, sb[2], 4 * nmu))) return rc;
+    if ((rc = ensure(ctx, sb[3], 8 * nm1))) return rc;
+    if ((rc = ensure(ctx, sb[4], 8 * nm1))) return rc;
+    if ((rc = ensure(ctx, sb[5], 8 * 3 * np_))) return rc;
+    if ((rc = ensure(ctx, sb[6], 8 * 3 * np_))) return rc;
+    if ((rc = ensure(ctx, sb[7], 8 * 3 * np_))) return rc;
+    if ((rc = ensure(ctx, sb[8], 4 * np_))) return rc;
+    if (n_mut > 0) {
+        CK(cudaMemcpyAsync(sb[0].p, mut_pos, 8 * (size_t)n_mut, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sb[1].p, mut_aaf, 8 * (size_t)n_mut, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sb[2].p, mut_indel, 4 * (size_t)n_mut, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(sb[3].p, mut_seg, 8 * nm1, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sb[4].p, pair_seg, 8 * nm1, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sb[5].p, primer_start, 8 * 3 * np_, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sb[6].p, primer_stop, 8 * 3 * np_, cudaMemcpyHostToDevice, st));
+    const int threads = 128;
+    const long long blocks = (n_pairs + threads - 1) / threads;
+    k_annotate_mutations<<<(unsigned)blocks, threads, 0, st>>>(
+        (const long long*)sb[0].p, (const double*)sb[1].p, (const int32_t*)sb[2].p, (const long long*)sb[3].p,
+        (const long long*)sb[4].p, n_markers, (const long long*)sb[5].p, (const long long*)sb[6].p, n_primers, n_pairs,
+        (double*)sb[7].p, (int32_t*)sb[8].p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(max_aaf, sb[7].p, 8 * 3 * np_, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(max_indel, sb[8].p, 4 * np_, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PO_OK;
+}

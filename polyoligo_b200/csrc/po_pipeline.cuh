@@ -260,3 +260,103 @@ __global__ void k_gather_tm(const double* __restrict__ tF, const double* __restr
     het2[2 * t] = h1[t].tm;
     het2[2 * t + 1] = h2 ? h2[t].tm : 0.0;
 }
+
+// Biopython 1.76 MeltingTemp.Tm_NN with default arguments and a perfect complement
+// (reference lib_markers.py:586-587).  Sums run in Biopython's order, in kcal/mol and
+// cal/(mol K) doubles, so the result is the same double Python computes.
+struct TmNNConsts {
+    double log_mon;   // math.log((Na + K + Tris / 2.0) * 1e-3)
+    double r_log_k;   // 1.987 * math.log((dnac1 - dnac2 / 2.0) * 1e-9)
+};
+__constant__ double c_nn3_h[16] = {-7.9, -8.4, -7.8, -7.2, -8.5, -8.0, -10.6, -7.8, -8.2, -9.8, -8.0, -8.4, -7.2, -8.2, -8.5, -7.9};
+__constant__ double c_nn3_s[16] = {-22.2, -22.4, -21.0, -20.4, -22.7, -19.9, -27.2, -21.0, -22.2, -24.4, -19.9, -22.4, -21.3, -22.2, -22.7, -22.2};
+
+__device__ __forceinline__ int ascii_code(char ch) {
+    switch (ch) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;  // _check() maps U to T
+    }
+    return -1;
+}
+
+__global__ void k_tm_nn(const char* __restrict__ ascii, const long long* __restrict__ off, long long n,
+                        const TmNNConsts K, double* __restrict__ tm) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const char* s = ascii + off[t];
+    const int len = (int)(off[t + 1] - off[t]);
+    double dh = 0.0, ds = 0.0;
+    bool bad = len < 1;
+    int first = 0, last = 0, prev = 0;
+    for (int k = 0; k < len; ++k) {
+        const int c = ascii_code(s[k]);
+        if (c < 0) {
+            bad = true;
+            break;
+        }
+        if (k == 0) first = c;
+        else {  // the 'zipping': nearest-neighbour sum along the sequence
+            dh += c_nn3_h[4 * prev + c];
+            ds += c_nn3_s[4 * prev + c];
+        }
+        prev = c;
+        last = c;
+    }
+    if (bad) {
+        tm[t] = nan("");
+        return;
+    }
+    // Biopython adds the initiation terms BEFORE zipping; addition order matters for the
+    // last bit, so rebuild the sums in its order: init terms first, then the dinucleotides.
+    const int at = (first == 0 || first == 3) + (last == 0 || last == 3);
+    const int gc = 2 - at;
+    double h = 0.0, sS = 0.0;
+    h += 2.3 * at;
+    sS += 4.1 * at;
+    h += 0.1 * gc;
+    sS += -2.8 * gc;
+    prev = first;
+    for (int k = 1; k < len; ++k) {
+        const int c = ascii_code(s[k]);
+        h += c_nn3_h[4 * prev + c];
+        sS += c_nn3_s[4 * prev + c];
+        prev = c;
+    }
+    const double corr = 0.368 * (len - 1) * K.log_mon;
+    sS += corr;
+    tm[t] = (1000 * h) / (sS + K.r_log_k) - 273.15;
+}
+
+// PrimerPair.add_mutations, numeric part (reference lib_primer3.py:166-210)
+__global__ void k_annotate_mutations(const long long* __restrict__ mut_pos, const double* __restrict__ mut_aaf,
+                                     const int32_t* __restrict__ mut_indel, const long long* __restrict__ mut_seg,
+                                     const long long* __restrict__ pair_seg, long long n_markers,
+                                     const long long* __restrict__ pstart, const long long* __restrict__ pstop,
+                                     int n_primers, long long n_pairs, double* __restrict__ max_aaf,
+                                     int32_t* __restrict__ max_indel) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    long long lo = 0, hi = n_markers - 1;  // marker of this pair: last m with pair_seg[m] <= t
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) >> 1;
+        if (pair_seg[mid] <= t) lo = mid;
+        else hi = mid - 1;
+    }
+    const long long ms = mut_seg[lo], me = mut_seg[lo + 1];
+    double aaf[3] = {0.0, 0.0, 0.0};
+    int indel = 0;
+    const long long w0 = pstart[3 * t], w1 = pstop[3 * t + 1];  // product window: F.start .. R.stop
+    for (long long m = ms; m < me; ++m) {
+        const long long pos = mut_pos[m];
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+            if (d < n_primers && pos >= pstart[3 * t + d] && pos <= pstop[3 * t + d]) aaf[d] = fmax(aaf[d], mut_aaf[m]);
+        if (pos >= w0 && pos <= w1) indel = max(indel, mut_indel[m]);
+    }
+    max_aaf[3 * t] = aaf[0];
+    max_aaf[3 * t + 1] = aaf[1];
+    max_aaf[3 * t + 2] = n_primers > 2 ? aaf[2] : 0.0;
+    max_indel[t] = indel;
+}

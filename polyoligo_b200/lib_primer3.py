@@ -267,3 +267,47 @@ def open_marker_window(hroi):
         start = min(1, hroi.start - size)
         stop = max(len(mmap), hroi.start + size)
         mmap[start:stop] = True
+
+
+# ---- "next" rows: mutation annotation and HRM product Tm ----------------
+def add_mutations_batch(pcrs, mutations_per_pcr, device=None):
+    """Numeric part of PrimerPair.add_mutations (reference lib_primer3.py:166-210) for many
+    markers: fills primers[d].max_aaf and pp.max_indel_size.  ``mutations_per_pcr[m]`` is the
+    mutation list (objects with pos / aaf / indel_size) of pcrs[m].  The mutation text and the
+    IUPAC-ambiguous primer strings stay with the reference's report writer."""
+    pps = [pp for pcr in pcrs for pp in pcr.pps]
+    if not pps:
+        return
+    keys = list(pps[0].primers.keys())
+    order = [k for k in ("F", "R", "A") if k in keys]
+    pair_seg = np.zeros(len(pcrs) + 1, dtype=np.int64)
+    np.cumsum([len(pcr.pps) for pcr in pcrs], out=pair_seg[1:])
+    mut_seg = np.zeros(len(pcrs) + 1, dtype=np.int64)
+    np.cumsum([len(m) for m in mutations_per_pcr], out=mut_seg[1:])
+    muts = [m for ml in mutations_per_pcr for m in ml]
+    start = np.zeros((len(pps), 3), dtype=np.int64)
+    stop = np.full((len(pps), 3), -1, dtype=np.int64)
+    for k, pp in enumerate(pps):
+        for c, d in enumerate(order):
+            start[k, c], stop[k, c] = pp.primers[d].start, pp.primers[d].stop
+    aaf, indel = get_context(device).annotate_mutations(
+        [m.pos for m in muts], [m.aaf for m in muts], [m.indel_size for m in muts], mut_seg, pair_seg, start, stop,
+        len(order))
+    for k, pp in enumerate(pps):
+        for c, d in enumerate(order):
+            pp.primers[d].max_aaf = max(pp.primers[d].max_aaf, float(aaf[k, c]))
+        pp.max_indel_size = max(pp.max_indel_size, int(indel[k]))
+
+
+def hrm_temps_batch(ref_products, alt_products, device=None):
+    """PCRproduct.get_hrm_temps (reference lib_markers.py:518-529) for many products:
+    list of {"ref", "alt", "delta"} with the reference's round_tidy digits."""
+    n = len(ref_products)
+    tm = get_context(device).tm_nn_batch(list(ref_products) + list(alt_products))
+    out = []
+    for r, a in zip(tm[:n], tm[n:]):
+        if np.isnan(r) or np.isnan(a):
+            raise ValueError("Base not allowed for Tm_NN")          # what Biopython raises
+        out.append({"ref": lib_utils.round_tidy(r, 4), "alt": lib_utils.round_tidy(a, 4),
+                    "delta": lib_utils.round_tidy(np.abs(r - a), 2)})
+    return out

@@ -243,6 +243,40 @@ def golden_masks(rng):
     dump("masks.json", {"cases": cases, "reduce_ivs": ivs})
 
 
+def golden_mutations(rng):
+    """8f-3: PrimerPair.add_mutations (reference lib_primer3.py:166-210), PCR and KASP pairs."""
+    import polyoligo.lib_vcf as lv
+    cases = []
+    for k in range(40):
+        kasp = k % 2 == 1
+        start = int(rng.integers(1000, 50000))
+        muts = []
+        for pos in np.sort(rng.choice(np.arange(start, start + 400), int(rng.integers(0, 12)), replace=False)):
+            ref = rand_seq(rng, int(rng.choice([1, 1, 1, 2, 4])))
+            alt = [rand_seq(rng, int(rng.choice([1, 1, 2, 60])))]
+            muts.append(lv.Mutation("chrT", int(pos), ref, alt, aaf=float(rng.choice([0.0, 0.02, 0.099, 0.1, 0.4]))))
+        pp = lk.PrimerPair() if kasp else lp.PrimerPair()
+        fs = start + int(rng.integers(0, 100))
+        fl, rl = int(rng.integers(18, 26)), int(rng.integers(18, 26))
+        rs = fs + int(rng.integers(60, 250))
+        pp.primers["F"].sequence = rand_seq(rng, fl)
+        pp.primers["F"].start, pp.primers["F"].stop = fs, fs + fl - 1
+        pp.primers["R"].sequence = rand_seq(rng, rl)
+        pp.primers["R"].start, pp.primers["R"].stop = rs, rs + rl - 1
+        if kasp:
+            pp.dir = "F" if k % 4 == 1 else "R"
+            pp.primers["A"].sequence = pp.primers[pp.dir].sequence[:-1] + "A"
+            pp.primers["A"].start, pp.primers["A"].stop = pp.primers[pp.dir].start, pp.primers[pp.dir].stop
+        pp.add_mutations(muts)
+        keys = ["F", "R", "A"] if kasp else ["F", "R"]
+        cases.append({"kasp": kasp, "mutations": [[m.pos, m.aaf, int(m.indel_size)] for m in muts],
+                      "start": [int(pp.primers[d].start) for d in keys],
+                      "stop": [int(pp.primers[d].stop) for d in keys],
+                      "max_aaf": [float(pp.primers[d].max_aaf) for d in keys],
+                      "max_indel": int(pp.max_indel_size)})
+    dump("mutations.json", {"cases": cases})
+
+
 if __name__ == "__main__":
     rng = np.random.default_rng(20240608)
     golden_marker_primers(rng)
@@ -250,3 +284,4 @@ if __name__ == "__main__":
     golden_heterodimer(rng)
     golden_scoring(rng)
     golden_masks(rng)
+    golden_mutations(np.random.default_rng(20240609))
