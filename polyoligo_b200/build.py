@@ -31,20 +31,25 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, out=None, defines=()):
+    """``out`` / ``defines`` build an alternate library (A/B experiments, selected at run
+    time with POLYOLIGO_B200_LIB); the default builds the in-tree product library."""
+    if out is None and not force and not stale():
         return LIB
+    out = out or LIB
     cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-fmad=false", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-shared", "-cudart", "static",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(LIB)
+    args = [a for a in sys.argv[1:] if not a.startswith("-D") and not a.startswith("--out=")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in args, verbose="-v" in args, out=outs[0] if outs else None,
+                defines=[a[2:] for a in sys.argv[1:] if a.startswith("-D")]))

@@ -27,6 +27,16 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
     __syncthreads();
 }
 
+// lanes per concurrently relaxed cell (see Grp<G> in po_thal.cuh).  Measured on B200 with
+// config 4 (3M pairs): dimer 16 lanes x 2 cells 226.8 ms vs 32 x 1 241.8 ms vs 8 x 4 252.4 ms;
+// hairpin 32 x 1 210.3 ms vs 16 x 2 224.4 ms vs 8 x 4 254.3 ms (fewer candidates per cell).
+#ifndef PO_HAIRPIN_GROUP
+#define PO_HAIRPIN_GROUP 32
+#endif
+#ifndef PO_DIMER_GROUP
+#define PO_DIMER_GROUP 16
+#endif
+
 // Work distribution: every warp pulls the next item from a global counter, so
 // long pairs do not stall a fixed partition.  Items whose finite-cell count
 // exceeds CAP are appended to `overflow` and picked up by the large-CAP pass.
@@ -65,7 +75,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                 if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
                 continue;
             }
-            thal_hairpin_warp<CAP, COUNT>(*tb, *xt, TA, gt, ws, oa, K, out + item, relax);
+            thal_hairpin_warp<PO_HAIRPIN_GROUP, CAP, COUNT>(*tb, *xt, TA, gt, ws, oa, K, out + item, relax);
         } else {
             const uint4 ob = B ? B[item] : oa;
             int a1, c1, g1, t1, a2, c2, g2, t2;
@@ -76,7 +86,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                 if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
                 continue;
             }
-            thal_dimer_warp<CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, out + item, relax);
+            thal_dimer_warp<PO_DIMER_GROUP, CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, out + item, relax);
         }
     }
 }

@@ -2,9 +2,11 @@
 // warp.  Restates upstream thal.c: initMatrix, fillMatrix (LSH, maxTM,
 // calc_bulge_internal), the RSH end scan, traceback and drawDimer.
 //
-// Control flow is kept warp-uniform (loops run a uniform number of trips with
-// clamped indices and predicated stores): a lane that leaves a loop early would
-// spin on the next warp barrier and burn issue slots.
+// The cells of one row do not depend on each other, so the warp relaxes 32/G of
+// them side by side, one group of G lanes each (Grp<G>).  Control flow is kept
+// warp-uniform (loops run a uniform number of trips with clamped indices and
+// predicated stores): a lane that leaves a loop early would spin on the next
+// warp barrier and burn issue slots.
 #pragma once
 #include "po_thal.cuh"
 
@@ -16,14 +18,14 @@ struct DimerCellCtx {
 // upstream calc_bulge_internal(pi, pj, ci, cj): value {dH,dS} of reaching the
 // cell through the loop that starts at list entry kp; {inf,-1} when rejected.
 template <int CAP>
-__device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const DimerWs<CAP>& ws, const DimerCellCtx& c,
-                                                    int kp, int* key_out) {
+__device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const DimerWs<CAP>& ws, const double2* ycell,
+                                                    const DimerCellCtx& c, int kp, int* key_out) {
     const uint32_t code = ws.code[kp];
     const double2 pv = ws.cell[kp];
     const int pb = CODE_B(code);
     const int l1 = c.ci - CODE_I(code) - 1, l2 = c.cj - CODE_J(code) - 1;
     // stack[s1[pi]][s1[ci]][s2[pj]][s2[cj]] = pb*64 + cb*16 + (3-pb)*4 + c2
-    const LoopOps o = loop_ops(A, ws.ycell, l1, l2, CODE_TQ(code), pb, pb * 60 + 12 + c.b1q);
+    const LoopOps o = loop_ops(A, ycell, l1, l2, CODE_TQ(code), pb, pb * 60 + 12 + c.b1q);
     *key_out = o.key;
     double H = (o.L.x + o.P.x) + o.C.x;
     double S = ((o.L.y + o.P.y) + o.C.y) + o.asymS;
@@ -45,17 +47,13 @@ __device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const Dime
 }
 
 // Candidate predecessors of cell (ci,cj): every finite (pi,pj) with pi < ci,
-// pj < cj and 1 <= (ci-pi-1)+(cj-pj-1) <= max_loop.  Lane l owns row ci-1-l;
-// the row's candidates are one contiguous run of the row-major list, described
-// by the lane's registers {incl, cnt, first} (see run_lookup).  Also publishes
-// the cell-side loop operands (ycell): every lane stores the same four values,
-// so each lane later reads what it wrote itself and no barrier is needed.
-template <int CAP>
-__device__ __forceinline__ Runs dimer_build_runs(const SmemTables& tb, DimerWs<CAP>& ws, int lane, int ci, int cj,
-                                                 int max_loop, bool prune, DimerCellCtx* ctx) {
-    const int l1 = lane, r = ci - 1 - lane;
-    const bool have = (r >= 1) & (l1 <= max_loop);
-    const int rr = have ? r : 1;
+// pj < cj and 1 <= (ci-pi-1)+(cj-pj-1) <= max_loop.  Virtual run l1 owns row
+// ci-1-l1; the row's candidates are one contiguous range of the row-major list.
+// Fills the group's run table and cell-side loop operands (ycell, stored
+// identically by every lane of the group) and returns the number of candidates.
+template <int G, int CAP>
+__device__ __forceinline__ int dimer_build_runs(const Grp<G>& g, const SmemTables& tb, DimerWs<CAP>& ws, int ci, int cj,
+                                                int max_loop, bool prune, DimerCellCtx* ctx) {
     const int cb = ws.s1[ci], c2 = ws.s2[cj];
     const int q = quad(c2, ws.s2[cj - 1], cb, ws.s1[ci - 1]);
     const double2 y0 = tb.tstack[q], y3 = tb.stackint2[q];
@@ -63,40 +61,53 @@ __device__ __forceinline__ Runs dimer_build_runs(const SmemTables& tb, DimerWs<C
     // (dH = +inf never wins and never matches in the traceback): only bulges remain, i.e.
     // row ci-1 (l1 == 0) and column cj-1 (l2 == 0).
     const bool interior_ok = fin(y0.x) | fin(y3.x);
-    const int hi_col = (l1 == 0) ? cj - 2 : cj - 1;       // l1 + l2 >= 1
-    int lo_col = max(1, cj - 1 - (max_loop - l1));        // l1 + l2 <= max_loop
-    if (prune && !interior_ok && l1 > 0) lo_col = max(lo_col, cj - 1);
-    const unsigned long long rm = ws.mask[3 - ws.s1[rr]];
-    Runs R;
-    R.cnt = have ? __popcll(rm & bit_range(lo_col - 1, hi_col - 1)) : 0;
-    R.first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
-    R.incl = warp_scan_incl(R.cnt, lane);
-    R.total = __shfl_sync(FULL, R.incl, 31);
+    RunTable& rt = ws.runs[g.idx];
+    int carry = 0;
+#pragma unroll
+    for (int sl = 0; sl < 32 / G; ++sl) {
+        const int l1 = sl * G + g.lane, r = ci - 1 - l1;
+        const bool have = (r >= 1) & (l1 <= max_loop);
+        const int rr = have ? r : 1;
+        const int hi_col = (l1 == 0) ? cj - 2 : cj - 1;       // l1 + l2 >= 1
+        int lo_col = max(1, cj - 1 - (max_loop - l1));        // l1 + l2 <= max_loop
+        if (prune && !interior_ok && l1 > 0) lo_col = max(lo_col, cj - 1);
+        const unsigned long long rm = ws.mask[3 - ws.s1[rr]];
+        const int cnt = have ? __popcll(rm & bit_range(lo_col - 1, hi_col - 1)) : 0;
+        const int first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
+        const int incl = g.scan_incl(cnt) + carry;
+        rt.end[l1] = (uint16_t)incl;
+        rt.first[l1] = (uint16_t)first;
+        carry = g.shfl(incl, G - 1);
+    }
     const bool cAT = (cb == 0) | (cb == 3);
-    ws.ycell[0] = y0;
-    ws.ycell[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
-    ws.ycell[2] = make_double2(0.0, 0.0);
-    ws.ycell[3] = y3;
+    double2* yc = ws.ycell[g.idx];
+    yc[0] = y0;
+    yc[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
+    yc[2] = make_double2(0.0, 0.0);
+    yc[3] = y3;
     ctx->ci = ci;
     ctx->cj = cj;
     ctx->b1q = cb * 16 + c2;
-    return R;
+    g.sync();
+    return carry;
 }
 
-// Forward scan of the queue: every lane keeps its best (largest T, earliest key).
-template <int CAP>
-__device__ __forceinline__ void dimer_scan(const TabAddr& A, const DimerWs<CAP>& ws, const DimerCellCtx& c, int lane,
-                                           const Runs& R, double iH, double iS, double RC, int mode, double* bT,
-                                           int* bKey, double2* bV) {
-    const int total = R.total;
+// Forward scan of the group's candidates: every lane keeps its best (largest T,
+// earliest key).  `trip_total` is the warp-wide maximum candidate count.
+template <int G, int CAP>
+__device__ __forceinline__ void dimer_scan(const Grp<G>& g, const TabAddr& A, const DimerWs<CAP>& ws,
+                                           const DimerCellCtx& c, int total, int trip_total, double iH, double iS,
+                                           double RC, int mode, double* bT, int* bKey, double2* bV) {
+    const RunTable& rt = ws.runs[g.idx];
+    const double2* yc = ws.ycell[g.idx];
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 bestV = make_double2(PO_INF, -1.0);
-    for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
+    for (int t0 = 0; t0 < trip_total; t0 += G) {
+        const int t = t0 + g.lane;
         bool act = t < total;
         int key;
-        const double2 v = dimer_loop_value<CAP>(A, ws, c, run_lookup(R.incl, R.cnt, R.first, act ? t : 0), &key);
+        const double2 v = dimer_loop_value<CAP>(A, ws, yc, c, run_lookup(rt, act ? t : 0), &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
         if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
@@ -111,11 +122,14 @@ __device__ __forceinline__ void dimer_scan(const TabAddr& A, const DimerWs<CAP>&
     *bV = bestV;
 }
 
-template <int CAP, bool COUNT>
+template <int G, int CAP, bool COUNT>
 __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const TabAddr& A, DimerWs<CAP>& ws,
                                 const uint4 oa, const uint4 ob, const PoConsts& K, po_thal_out* out,
                                 unsigned long long* relax) {
     const int lane = threadIdx.x & 31;
+    const Grp<G> g = Grp<G>::make();
+    const Grp<32> gw = Grp<32>::make();
+    constexpr int NG = 32 / G;
     const int len1 = po_len(oa), len2 = po_len(ob);
     po_thal_out r;
     r.tm = 0.0;
@@ -167,7 +181,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         const int i0 = lane + 1, i1 = lane + 33;
         const int c0 = i0 <= len1 ? __popcll(ROWMASK(i0)) : 0;
         const int c1 = i1 <= len1 ? __popcll(ROWMASK(i1)) : 0;
-        const int x0 = warp_scan_incl(c0, lane), x1 = warp_scan_incl(c1, lane);
+        const int x0 = gw.scan_incl(c0), x1 = gw.scan_incl(c1);
         const int tot0 = __shfl_sync(FULL, x0, 31);
         ws.start[i0] = (uint16_t)(x0 - c0);
         if (i1 < 64) ws.start[i1] = (uint16_t)(tot0 + x1 - c1);
@@ -236,44 +250,62 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         }
         __syncwarp();
         if (i == 1) continue;
-        // phase B: bulges and interior loops, one cell at a time
-        for (int k = rs; k < re; ++k) {
+        // phase B: bulges and interior loops, 32/G cells of the row at a time (column 1 has
+        // no predecessor)
+        const int kb = rs + (int)(ROWMASK(i) & 1ull);
+        for (int k0 = kb; k0 < re; k0 += NG) {
+            const bool valid = k0 + g.idx < re;
+            const int k = valid ? k0 + g.idx : re - 1;
             const int j = CODE_J(ws.code[k]);
-            if (j == 1) continue;
             DimerCellCtx c;
-            const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, !COUNT, &c);
-            if (COUNT) cnt += (lane == 0) ? R.total : 0;
-            if (R.total == 0) continue;
-            const double2 cur = ws.cell[k];
-            const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
-            double bT, wT = -PO_INF;
-            int bKey, wKey = KEY_NONE;
-            double2 bV;
-            dimer_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
-            int src = warp_argmax(bT, bKey, &wT, &wKey);
-            if (src >= 0 && wKey == KEY_STAR) {
-                // The 1x1 loop is the arg-max.  Upstream accepts it only if it beats the
-                // running best by SMALL_NON_ZERO at the moment it is visited; re-derive that
-                // running best (current cell + the three candidates visited earlier).
-                double pT, qT = -PO_INF;
-                int pKey, qKey = KEY_NONE;
-                double2 pV;
-                dimer_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
-                const int psrc = warp_argmax(pT, pKey, &qT, &qKey);
-                const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
-                if (!((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm)) {
-                    dimer_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_NO_STAR, &bT, &bKey, &bV);
-                    src = warp_argmax(bT, bKey, &wT, &wKey);
+            int total = dimer_build_runs<G, CAP>(g, tb, ws, i, j, max_loop, !COUNT, &c);
+            total = valid ? total : 0;
+            if (COUNT) cnt += (g.lane == 0) ? total : 0;
+            const int trip_total = NG == 1 ? total : warp_max_int(total);
+            if (trip_total > 0) {
+                const double2 cur = ws.cell[k];
+                const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
+                double bT, wT = -PO_INF;
+                int bKey, wKey = KEY_NONE;
+                double2 bV;
+                dimer_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
+                int src = g.argmax(bT, bKey, &wT, &wKey);
+                const bool star = src >= 0 && wKey == KEY_STAR;
+                if (__any_sync(FULL, star)) {
+                    // The 1x1 loop is the arg-max.  Upstream accepts it only if it beats the
+                    // running best by SMALL_NON_ZERO at the moment it is visited; re-derive that
+                    // running best (current cell + the three candidates visited earlier).
+                    double pT, qT = -PO_INF;
+                    int pKey, qKey = KEY_NONE;
+                    double2 pV;
+                    dimer_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
+                    const int psrc = g.argmax(pT, pKey, &qT, &qKey);
+                    const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
+                    const bool redo = star && !((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm);
+                    if (__any_sync(FULL, redo)) {
+                        double nT, xT = -PO_INF;
+                        int nKey, xKey = KEY_NONE;
+                        double2 nV;
+                        dimer_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_NO_STAR, &nT, &nKey, &nV);
+                        const int nsrc = g.argmax(nT, nKey, &xT, &xKey);
+                        if (redo) {
+                            bV = nV;
+                            src = nsrc;
+                            wT = xT;
+                            wKey = xKey;
+                        }
+                    }
+                }
+                double H = g.shfl(bV.x, max(src, 0)), S = g.shfl(bV.y, max(src, 0));
+                if (src >= 0 && wT > Tcur) {
+                    if (S < PO_MIN_ENTROPY_CUTOFF) {
+                        S = PO_MIN_ENTROPY;
+                        H = 0.0;
+                    }
+                    if (fin(H)) ws.cell[k] = make_double2(H, S);  // the group's lanes store the same value
                 }
             }
-            if (src >= 0 && wT > Tcur) {
-                double H = shfl_d(bV.x, src), S = shfl_d(bV.y, src);
-                if (S < PO_MIN_ENTROPY_CUTOFF) {
-                    S = PO_MIN_ENTROPY;
-                    H = 0.0;
-                }
-                if (fin(H)) ws.cell[k] = make_double2(H, S);  // every lane stores the same value: no barrier
-            }
+            __syncwarp();  // run tables are rewritten by the next batch
         }
     }
 
@@ -297,7 +329,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
     if (COUNT) cnt += (lane == 0) ? len1 * len2 : 0;
     double wG = PO_INF;
     int wK = KEY_NONE;
-    const int gsrc = warp_argmin(bestG, bestK, &wG, &wK);
+    const int gsrc = gw.argmin(bestG, bestK, &wG, &wK);
     if (COUNT && relax) {
         __syncwarp();
         const unsigned total_cnt = __reduce_add_sync(FULL, (unsigned)cnt);
@@ -342,19 +374,19 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         // loops: first candidate in upstream order whose value reproduces the cell
         const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
         DimerCellCtx c;
-        const Runs R = dimer_build_runs<CAP>(tb, ws, lane, i, j, max_loop, true, &c);
+        const int total = dimer_build_runs<32, CAP>(gw, tb, ws, i, j, max_loop, true, &c);
         int myKey = KEY_NONE;
-        for (int t0 = 0; t0 < R.total; t0 += 32) {
+        for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
-            const bool act = t < R.total;
+            const bool act = t < total;
             int key;
-            const double2 v = dimer_loop_value<CAP>(A, ws, c, run_lookup(R.incl, R.cnt, R.first, act ? t : 0), &key);
+            const double2 v = dimer_loop_value<CAP>(A, ws, ws.ycell[0], c, run_lookup(ws.runs[0], act ? t : 0), &key);
             const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
             // traceback mode of the 1x1 branch reports its value only when T1 >= T2
             const bool ok = act & (key < myKey) & ((key != KEY_STAR) | (T1 >= Tcur));
             if (ok && eq5(cur.y, v.y) && eq5(cur.x, v.x)) myKey = key;
         }
-        const int wKey = warp_min_int(myKey);
+        const int wKey = gw.min_s32(myKey);
         if (wKey == KEY_NONE) break;  // guard: upstream would spin here (unreachable for <= 60 nt)
         const int sum = wKey >> 6, l1 = wKey & 63;
         i = i - l1 - 1;
@@ -368,10 +400,10 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
     // ---- drawDimer ---------------------------------------------------------------
     const int N = npairs - 1;  // (2 * npairs) / 2 - 1
     const double t = (dH / (dS + (N * K.salt_corr) + RC)) - PO_ABSOLUTE_ZERO;
-    const double G = dH - (K.temp_k * (dS + (N * K.salt_corr)));
+    const double dG = dH - (K.temp_k * (dS + (N * K.salt_corr)));
     const double S = dS + (N * K.salt_corr);
     r.tm = t;
-    r.dg = G;
+    r.dg = dG;
     r.dh = dH;
     r.ds = S;
     r.flags = PO_ITEM_STRUCTURE_FOUND | (sym ? PO_ITEM_SYMMETRIC : 0);

@@ -5,8 +5,10 @@
 //
 // Finite cells (i,j): j - i >= 4 and bases complementary.  They are kept in
 // upstream's fill order (j ascending, i descending), so the cells enclosed by
-// (i,j) are a prefix of the list.  Control flow is kept warp-uniform (see
-// po_thal_dimer.cuh).
+// (i,j) are a prefix of the list.  The cells of one column do not depend on
+// each other, so the warp relaxes 32/G of them side by side, one group of G
+// lanes each (Grp<G>); control flow stays warp-uniform (uniform trip counts,
+// clamped indices, predicated stores).
 #pragma once
 #include "po_thal.cuh"
 
@@ -23,13 +25,13 @@ struct HairpinCellCtx {
 // in the same association order.  In upstream's sums the closing pair's term
 // comes first, the enclosed pair's second.
 template <int CAP>
-__device__ __forceinline__ double2 hairpin_loop_term(const TabAddr& A, const HairpinWs<CAP>& ws,
+__device__ __forceinline__ double2 hairpin_loop_term(const TabAddr& A, const HairpinWs<CAP>& ws, const double2* ycell,
                                                      const HairpinCellCtx& c, int kp, int* key_out) {
     const uint32_t code = ws.code[kp];
     const int b = CODE_B(code);
     const int l1 = CODE_I(code) - c.i - 1, l2 = c.j - CODE_J(code) - 1;
     // stack[s[i]][s[ii]][s[j]][s[jj]] = bi*64 + b*16 + bj*4 + (3-b)
-    const LoopOps o = loop_ops(A, ws.ycell, l1, l2, CODE_TQ(code), b, c.b1q + b * 15 + 3);
+    const LoopOps o = loop_ops(A, ycell, l1, l2, CODE_TQ(code), b, c.b1q + b * 15 + 3);
     *key_out = o.key;
     // bulge of one: upstream sums bulge + stack only; otherwise closing side, then enclosed side
     const double H = o.isB1 ? (o.L.x + o.P.x) + o.C.x : (o.L.x + o.C.x) + o.P.x;
@@ -123,58 +125,68 @@ __device__ __forceinline__ bool hp_finite(const HairpinWs<CAP>& ws, int i, int j
 }
 
 // Candidates enclosed by (i,j): every finite (ii,jj) with i < ii, jj < j and
-// 1 <= (ii-i-1)+(j-jj-1) <= max_loop.  Lane l owns column j-1-l; the column's
-// candidates are one contiguous run of the list (rows descending), described by
-// the lane's registers (see run_lookup).  Also publishes the closing-pair loop
-// operands (ycell), stored identically by every lane (no barrier needed).
-template <int CAP>
-__device__ __forceinline__ Runs hairpin_build_runs(const SmemTables& tb, HairpinWs<CAP>& ws, int lane, int i, int j,
-                                                   int max_loop, bool prune, HairpinCellCtx* ctx) {
-    const int l2 = lane, jj = j - 1 - lane;
-    const bool have = (jj >= 5) & (l2 <= max_loop);
-    const int jc = have ? jj : 5;
+// 1 <= (ii-i-1)+(j-jj-1) <= max_loop.  Virtual run l2 owns column j-1-l2; the
+// column's candidates are one contiguous range of the list (rows descending).
+// Fills the group's run table and closing-pair loop operands (ycell, stored
+// identically by every lane of the group) and returns the number of candidates.
+template <int G, int CAP>
+__device__ __forceinline__ int hairpin_build_runs(const Grp<G>& g, const SmemTables& tb, HairpinWs<CAP>& ws, int i,
+                                                  int j, int max_loop, bool prune, HairpinCellCtx* ctx) {
     const int bi = ws.s1[i], bj = ws.s1[j];
     const int q = quad(bi, ws.s1[i + 1] & 3, bj, ws.s1[j - 1] & 3);
     const double2 y0 = tb.tstack[q], y3 = tb.stackint2[q];
     // both closing-pair terms infinite: only bulges (l2 == 0 or l1 == 0) can be finite
     const bool interior_ok = fin(y0.x) | fin(y3.x);
-    const int lo_row = (l2 == 0) ? i + 2 : i + 1;            // l1 + l2 >= 1
-    int hi_row = min(jc - 4, i + 1 + (max_loop - l2));        // l1 + l2 <= max_loop
-    if (prune && !interior_ok && l2 > 0) hi_row = min(hi_row, i + 1);
-    const unsigned long long cm = HP_COLMASK(ws, jc);
-    Runs R;
-    R.cnt = have ? __popcll(cm & bit_range(lo_row - 1, hi_row - 1)) : 0;
-    R.first = ws.start[jc] + __popcll(cm >> min(max(hi_row, 0), 63));
-    R.incl = warp_scan_incl(R.cnt, lane);
-    R.total = __shfl_sync(FULL, R.incl, 31);
+    RunTable& rt = ws.runs[g.idx];
+    int carry = 0;
+#pragma unroll
+    for (int sl = 0; sl < 32 / G; ++sl) {
+        const int l2 = sl * G + g.lane, jj = j - 1 - l2;
+        const bool have = (jj >= 5) & (l2 <= max_loop);
+        const int jc = have ? jj : 5;
+        const int lo_row = (l2 == 0) ? i + 2 : i + 1;            // l1 + l2 >= 1
+        int hi_row = min(jc - 4, i + 1 + (max_loop - l2));        // l1 + l2 <= max_loop
+        if (prune && !interior_ok && l2 > 0) hi_row = min(hi_row, i + 1);
+        const unsigned long long cm = HP_COLMASK(ws, jc);
+        const int cnt = have ? __popcll(cm & bit_range(lo_row - 1, hi_row - 1)) : 0;
+        const int first = ws.start[jc] + __popcll(cm >> min(max(hi_row, 0), 63));
+        const int incl = g.scan_incl(cnt) + carry;
+        rt.end[l2] = (uint16_t)incl;
+        rt.first[l2] = (uint16_t)first;
+        carry = g.shfl(incl, G - 1);
+    }
     const bool cAT = (bi == 0) | (bi == 3);
-    ws.ycell[0] = y0;
-    ws.ycell[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
-    ws.ycell[2] = make_double2(0.0, 0.0);
-    ws.ycell[3] = y3;
+    double2* yc = ws.ycell[g.idx];
+    yc[0] = y0;
+    yc[1] = make_double2(cAT ? PO_AT_H : 0.0, cAT ? PO_AT_S : 0.0);
+    yc[2] = make_double2(0.0, 0.0);
+    yc[3] = y3;
     ctx->i = i;
     ctx->j = j;
     ctx->b1q = bi * 64 + bj * 4;
-    return R;
+    g.sync();
+    return carry;
 }
 
-// Scan of the queue.  SCAN_LAST_GE selects the LAST candidate (largest key)
-// with T1 >= Tcur, which is what upstream's CBI(traceback = 2) leaves in its
-// output argument.
-template <int CAP>
-__device__ __forceinline__ void hairpin_scan(const TabAddr& A, const HairpinWs<CAP>& ws, const HairpinCellCtx& c,
-                                             int lane, const Runs& R, double iH, double iS, double RC, int mode,
-                                             double Tcur, double* bT, int* bKey, double2* bV) {
-    const int total = R.total;
+// Scan of the group's candidates; `trip_total` is the warp-wide maximum of the
+// groups' candidate counts (uniform trip count).  SCAN_LAST_GE selects the LAST
+// candidate (largest key) with T1 >= Tcur, which is what upstream's
+// CBI(traceback = 2) leaves in its output argument.
+template <int G, int CAP>
+__device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, const HairpinWs<CAP>& ws,
+                                             const HairpinCellCtx& c, int total, int trip_total, double iH, double iS,
+                                             double RC, int mode, double Tcur, double* bT, int* bKey, double2* bV) {
+    const RunTable& rt = ws.runs[g.idx];
+    const double2* yc = ws.ycell[g.idx];
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 bestV = make_double2(PO_INF, -1.0);
-    for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
+    for (int t0 = 0; t0 < trip_total; t0 += G) {
+        const int t = t0 + g.lane;
         bool act = t < total;
-        const int kp = run_lookup(R.incl, R.cnt, R.first, act ? t : 0);
+        const int kp = run_lookup(rt, act ? t : 0);
         int key;
-        double2 v = hairpin_loop_term<CAP>(A, ws, c, kp, &key);
+        double2 v = hairpin_loop_term<CAP>(A, ws, yc, c, kp, &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
         if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double2 pv = ws.cell[kp];
@@ -265,9 +277,9 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
     // arg-max inside each 8-lane group
 #pragma unroll
     for (int m = 4; m >= 1; m >>= 1) {
-        const double ot = shfl_xor_d(bestT, m);
+        const double ot = __shfl_xor_sync(FULL, bestT, m);
         const int ok = __shfl_xor_sync(FULL, bestKey, m);
-        const double oh = shfl_xor_d(best.x, m), os = shfl_xor_d(best.y, m);
+        const double oh = __shfl_xor_sync(FULL, best.x, m), os = __shfl_xor_sync(FULL, best.y, m);
         if ((ot > bestT) | ((ot == bestT) & (ok < bestKey))) {
             bestT = ot;
             bestKey = ok;
@@ -277,11 +289,14 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
     return best;
 }
 
-template <int CAP, bool COUNT>
+template <int G, int CAP, bool COUNT>
 __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, const TabAddr& A, const PoTables* gt,
                                   HairpinWs<CAP>& ws, const uint4 oa, const PoConsts& K, po_thal_out* out,
                                   unsigned long long* relax) {
     const int lane = threadIdx.x & 31;
+    const Grp<G> g = Grp<G>::make();
+    const Grp<32> gw = Grp<32>::make();
+    constexpr int NG = 32 / G;
     const int len = po_len(oa);
     po_thal_out r;
     r.tm = 0.0;
@@ -312,7 +327,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
         const int j0 = lane + 1, j1 = lane + 33;
         const int c0 = j0 <= len ? __popcll(HP_COLMASK(ws, j0)) : 0;
         const int c1 = j1 <= len ? __popcll(HP_COLMASK(ws, j1)) : 0;
-        const int x0 = warp_scan_incl(c0, lane), x1 = warp_scan_incl(c1, lane);
+        const int x0 = gw.scan_incl(c0), x1 = gw.scan_incl(c1);
         const int tot0 = __shfl_sync(FULL, x0, 31);
         ws.start[j0] = (uint16_t)(x0 - c0);
         if (j1 < 64) ws.start[j1] = (uint16_t)(tot0 + x1 - c1);
@@ -367,43 +382,61 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             if (act) ws.cell[k] = (T1 > T0) ? make_double2(H1, S1) : make_double2(H0, S0);
         }
         __syncwarp();
-        // phase B: CBI, one cell at a time
-        for (int k = cs; k < ce; ++k) {
+        // phase B: CBI, 32/G cells of the column at a time.  Cells with j - i < 7 have no room
+        // for an enclosed pair plus a loop; rows descend along the list, so they come first.
+        const int kb = j >= 8 ? cs + __popcll(HP_COLMASK(ws, j) >> (j - 7)) : ce;
+        for (int k0 = kb; k0 < ce; k0 += NG) {
+            const bool valid = k0 + g.idx < ce;
+            const int k = valid ? k0 + g.idx : ce - 1;
             const int i = CODE_I(ws.code[k]);
-            if (j - i < 7) continue;  // no room for an enclosed pair plus a loop
             HairpinCellCtx c;
-            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, !COUNT, &c);
-            if (COUNT) cnt += (lane == 0) ? R.total : 0;
-            if (R.total == 0) continue;
-            const double2 cur = ws.cell[k];
-            const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
-            double bT, wT = -PO_INF;
-            int bKey, wKey = KEY_NONE;
-            double2 bV;
-            hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
-            int src = warp_argmax(bT, bKey, &wT, &wKey);
-            if (src >= 0 && wKey == KEY_STAR) {
-                double pT, qT = -PO_INF;
-                int pKey, qKey = KEY_NONE;
-                double2 pV;
-                hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey, &pV);
-                const int psrc = warp_argmax(pT, pKey, &qT, &qKey);
-                const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
-                if (!((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm)) {
-                    hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_NO_STAR, Tcur, &bT, &bKey, &bV);
-                    src = warp_argmax(bT, bKey, &wT, &wKey);
+            int total = hairpin_build_runs<G, CAP>(g, tb, ws, i, j, max_loop, !COUNT, &c);
+            total = valid ? total : 0;
+            if (COUNT) cnt += (g.lane == 0) ? total : 0;
+            const int trip_total = NG == 1 ? total : warp_max_int(total);
+            if (trip_total > 0) {
+                const double2 cur = ws.cell[k];
+                const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
+                double bT, wT = -PO_INF;
+                int bKey, wKey = KEY_NONE;
+                double2 bV;
+                hairpin_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
+                int src = g.argmax(bT, bKey, &wT, &wKey);
+                const bool star = src >= 0 && wKey == KEY_STAR;
+                if (__any_sync(FULL, star)) {
+                    double pT, qT = -PO_INF;
+                    int pKey, qKey = KEY_NONE;
+                    double2 pV;
+                    hairpin_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey,
+                                         &pV);
+                    const int psrc = g.argmax(pT, pKey, &qT, &qKey);
+                    const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
+                    const bool redo = star && !((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm);
+                    if (__any_sync(FULL, redo)) {
+                        double nT, xT = -PO_INF;
+                        int nKey, xKey = KEY_NONE;
+                        double2 nV;
+                        hairpin_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_NO_STAR, Tcur, &nT, &nKey,
+                                             &nV);
+                        const int nsrc = g.argmax(nT, nKey, &xT, &xKey);
+                        if (redo) {
+                            bV = nV;
+                            src = nsrc;
+                            wT = xT;
+                            wKey = xKey;
+                        }
+                    }
                 }
-            }
-            if (src >= 0 && wT > Tcur) {
-                double H = shfl_d(bV.x, src), S = shfl_d(bV.y, src);
-                if (fin(H)) {
+                double H = g.shfl(bV.x, max(src, 0)), S = g.shfl(bV.y, max(src, 0));
+                if (src >= 0 && wT > Tcur && fin(H)) {
                     if (S < PO_MIN_ENTROPY_CUTOFF) {
                         S = PO_MIN_ENTROPY;
                         H = 0.0;
                     }
-                    ws.cell[k] = make_double2(H, S);  // every lane stores the same value: no barrier
+                    ws.cell[k] = make_double2(H, S);  // the group's lanes store the same value
                 }
             }
+            __syncwarp();  // run tables are rewritten by the next batch
         }
         // phase C: calc_hairpin, keep the lower dG of {loop closure, current value}
         for (int k0 = cs; k0 < ce; k0 += 32) {
@@ -441,7 +474,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const double2 e = end5_all<CAP>(tb, ws, lane, i, iH, iS, RC);
             const double T1 = po_div(hp + iH, sp + iS + RC);
             const double Tv = po_div(e.x + iH, e.y + iS + RC);
-            const double T2 = shfl_d(Tv, 0), T3 = shfl_d(Tv, 8), T4 = shfl_d(Tv, 16), T5 = shfl_d(Tv, 24);
+            const double T2 = gw.shfl(Tv, 0), T3 = gw.shfl(Tv, 8), T4 = gw.shfl(Tv, 16), T5 = gw.shfl(Tv, 24);
             int mx;
             if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
             else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
@@ -449,9 +482,9 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             else if (T4 > T5) mx = 4;
             else mx = 5;
             if (mx > 1) {
-                const double eh = shfl_d(e.x, (mx - 2) * 8), es = shfl_d(e.y, (mx - 2) * 8);
-                const double G = eh - (K.temp_k * es);
-                if (G < 0.0) {
+                const double eh = gw.shfl(e.x, (mx - 2) * 8), es = gw.shfl(e.y, (mx - 2) * 8);
+                const double Gv = eh - (K.temp_k * es);
+                if (Gv < 0.0) {
                     hn = eh;
                     sn = es;
                 }
@@ -533,7 +566,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
                     else if (act && eq5(si_, s1v) && eq5(hi_, h1v)) myKey = min(myKey, k * 2 + 1);
                 }
             }
-            const int wKey = warp_min_int(myKey);
+            const int wKey = gw.min_s32(myKey);
             if (wKey == KEY_NONE) continue;
             const int k = wKey >> 1;
             const int p = (v == 1 || v == 3) ? k + 1 : k + 2;
@@ -566,18 +599,18 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             if (j - i < 7) continue;
             const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
             HairpinCellCtx c;
-            const Runs R = hairpin_build_runs<CAP>(tb, ws, lane, i, j, max_loop, true, &c);
-            if (R.total == 0) continue;
+            const int total = hairpin_build_runs<32, CAP>(gw, tb, ws, i, j, max_loop, true, &c);
+            if (total == 0) continue;
             double bT;
             int bKey;
             double2 bV;
-            hairpin_scan<CAP>(A, ws, c, lane, R, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
+            hairpin_scan<32, CAP>(gw, A, ws, c, total, total, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
             // LAST candidate with T1 >= Tcur: largest key
-            const int mxKey = warp_max_int(bKey == KEY_NONE ? -1 : bKey);
+            const int mxKey = gw.max_s32(bKey == KEY_NONE ? -1 : bKey);
             if (mxKey < 0) continue;
             const unsigned who = __ballot_sync(FULL, bKey == mxKey);
             const int src = __ffs(who) - 1;
-            double H2 = shfl_d(bV.x, src), S2 = shfl_d(bV.y, src);
+            double H2 = gw.shfl(bV.x, src), S2 = gw.shfl(bV.y, src);
             if (fin(H2) && S2 < PO_MIN_ENTROPY_CUTOFF) {
                 S2 = PO_MIN_ENTROPY;
                 H2 = 0.0;
@@ -585,17 +618,17 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             if (!(eq5(cur.y, S2) && eq5(cur.x, H2))) continue;
             // first candidate (upstream order) whose value reproduces the cell
             int myKey = KEY_NONE;
-            for (int t0 = 0; t0 < R.total; t0 += 32) {
+            for (int t0 = 0; t0 < total; t0 += 32) {
                 const int t = t0 + lane;
-                const bool act = t < R.total;
-                const int kp = run_lookup(R.incl, R.cnt, R.first, act ? t : 0);
+                const bool act = t < total;
+                const int kp = run_lookup(ws.runs[0], act ? t : 0);
                 int key;
-                double2 v = hairpin_loop_term<CAP>(A, ws, c, kp, &key);
+                double2 v = hairpin_loop_term<CAP>(A, ws, ws.ycell[0], c, kp, &key);
                 v = hp_fix(v.x, v.y);  // traceback == 1 form: every branch reports its value
                 const double2 pv = ws.cell[kp];
                 if (act && key < myKey && eq5(cur.y, v.y + pv.y) && eq5(cur.x, v.x + pv.x)) myKey = key;
             }
-            const int wKey = warp_min_int(myKey);
+            const int wKey = gw.min_s32(myKey);
             if (wKey == KEY_NONE) continue;
             const int sum = wKey >> 6, l1 = wKey & 63;
             const int ii = i + l1 + 1, jj = j - (sum - l1) - 1;
