@@ -247,6 +247,74 @@ int po_annotate_mutations_batch(po_ctx *ctx, const int64_t *mut_pos, const doubl
                                 const int64_t *primer_start, const int64_t *primer_stop,
                                 int n_primers, double *max_aaf, int32_t *max_indel);
 
+/* ---- primer3-core style picking of the complementary primer ------------------
+ * Replaces primer3.bindings.designPrimers as reached from lib_primer3.get_primers
+ * (reference src/polyoligo/lib_primer3.py:466-529, globals set at :539-544; callers
+ * _lib_kasp.py:567-590 with SEQUENCE_PRIMER / SEQUENCE_PRIMER_REVCOMP fixed, _lib_pcr.py:
+ * 167-180 with both primers free).  libprimer3 is third-party and absent from the reference
+ * tree: the restated semantics (candidate filters, penalty, pair constraints, ordering) are
+ * listed in DESIGN.md section 7; parity with the real library is UNPINNED. */
+typedef struct {
+    int32_t min_size, opt_size, max_size;            /* PRIMER_{MIN,OPT,MAX}_SIZE                 */
+    int32_t num_return;                               /* PRIMER_NUM_RETURN                          */
+    double min_tm, opt_tm, max_tm;                    /* PRIMER_{MIN,OPT,MAX}_TM                    */
+    double min_gc, max_gc;                            /* PRIMER_{MIN,MAX}_GC                        */
+    double max_self_any_th, max_self_end_th, max_hairpin_th;      /* PRIMER_MAX_*_TH              */
+    double pair_max_compl_any_th, pair_max_compl_end_th;          /* PRIMER_PAIR_MAX_COMPL_*_TH   */
+    double pair_max_diff_tm;                          /* PRIMER_PAIR_MAX_DIFF_TM                    */
+    double wt_tm_gt, wt_tm_lt, wt_size_lt, wt_size_gt;            /* PRIMER_WT_*                  */
+    double mv_conc, dv_conc, dntp_conc, dna_conc;     /* PRIMER_SALT_*, PRIMER_DNTP_CONC, PRIMER_DNA_CONC */
+    int32_t max_poly_x, gc_clamp, max_end_gc;         /* PRIMER_MAX_POLY_X, PRIMER_GC_CLAMP, PRIMER_MAX_END_GC */
+    int32_t n_size_ranges;                            /* PRIMER_PRODUCT_SIZE_RANGE, tried in order  */
+    int32_t size_lo[8], size_hi[8];
+} po_p3_settings;
+
+typedef struct {
+    po_oligo seq;                 /* the primer, 5'->3'                                            */
+    double tm, gc_percent, penalty;
+    double self_any_th, self_end_th, hairpin_th;      /* NaN until evaluated (lazily, like libprimer3) */
+    int32_t start;                /* primer3 convention: index of the primer's 5' base on the template
+                                     (for a right primer that is its rightmost template base)        */
+    int32_t len;
+    int32_t set;                  /* template the oligo was cut from                                 */
+    int32_t flags;                /* PO_P3_*                                                          */
+} po_p3_oligo;                    /* 80 bytes                                                         */
+enum { PO_P3_OK = 1, PO_P3_SELF_DONE = 2, PO_P3_SELF_FAILED = 4, PO_P3_QUEUED = 8 };
+
+typedef struct {
+    int32_t set;                  /* template index                                                   */
+    int32_t side;                 /* 1: left primer given (SEQUENCE_PRIMER), 2: right primer given
+                                     (SEQUENCE_PRIMER_REVCOMP)                                        */
+    int32_t start, len;           /* the given primer on the template, primer3 convention            */
+} po_p3_task;
+
+typedef struct {
+    po_p3_oligo other;            /* the picked complementary primer                                  */
+    double pair_penalty, compl_any_th, compl_end_th;
+    int32_t product_size;
+    int32_t size_range;           /* index of the PRIMER_PRODUCT_SIZE_RANGE entry it was found in     */
+} po_p3_pair;                     /* 112 bytes                                                        */
+
+/* Candidate oligos of n_sets templates: every window of min..max_size nt that avoids masked
+ * bases (mask != 0: SEQUENCE_EXCLUDED_REGION / SEQUENCE_TARGET / outside SEQUENCE_INCLUDED_REGION)
+ * and non-ACGT letters and passes the GC, clamp, poly-X and Tm limits, with its penalty.
+ * Lists are sorted like libprimer3 sorts them (penalty, then start descending, then length):
+ * list 2*s = left primers of set s, list 2*s+1 = right primers.  list_off has 2*n_sets+1
+ * entries.  With out == NULL only list_off is produced (sizing call). */
+int po_p3_candidates_batch(po_ctx *ctx, const po_p3_settings *s, const char *tmpl, const uint8_t *mask,
+                           const int64_t *set_off, int64_t n_sets, int64_t *list_off,
+                           po_p3_oligo *out, int64_t out_cap);
+
+/* designPrimers with one primer fixed, for n_tasks (template, given primer) tasks: the best
+ * num_return complementary primers per task in libprimer3's order.  set_target is NULL or
+ * 2 x n_sets (start, len; len <= 0: none).  fixed_out (n_tasks) receives the given primer's own
+ * record (flags without PO_P3_OK: it violates the constraints and the task returns nothing);
+ * pairs_out is n_tasks x num_return, n_pairs_out the valid count per task. */
+int po_p3_design_fixed_batch(po_ctx *ctx, const po_p3_settings *s, const char *tmpl, const uint8_t *mask,
+                             const int64_t *set_off, const int32_t *set_target, int64_t n_sets,
+                             const po_p3_task *tasks, int64_t n_tasks, po_p3_oligo *fixed_out,
+                             po_p3_pair *pairs_out, int32_t *n_pairs_out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context has launched since po_init. */
 int64_t po_launch_count(const po_ctx *ctx);

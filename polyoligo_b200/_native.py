@@ -53,6 +53,31 @@ class ValidParams(C.Structure):
                 ("tm_delta", C.c_double)]
 
 
+class P3Settings(C.Structure):
+    """po_p3_settings; defaults are libprimer3's (version-2 defaults, thermodynamic alignment)."""
+    _fields_ = [("min_size", C.c_int32), ("opt_size", C.c_int32), ("max_size", C.c_int32), ("num_return", C.c_int32),
+                ("min_tm", C.c_double), ("opt_tm", C.c_double), ("max_tm", C.c_double),
+                ("min_gc", C.c_double), ("max_gc", C.c_double),
+                ("max_self_any_th", C.c_double), ("max_self_end_th", C.c_double), ("max_hairpin_th", C.c_double),
+                ("pair_max_compl_any_th", C.c_double), ("pair_max_compl_end_th", C.c_double),
+                ("pair_max_diff_tm", C.c_double),
+                ("wt_tm_gt", C.c_double), ("wt_tm_lt", C.c_double), ("wt_size_lt", C.c_double),
+                ("wt_size_gt", C.c_double),
+                ("mv_conc", C.c_double), ("dv_conc", C.c_double), ("dntp_conc", C.c_double), ("dna_conc", C.c_double),
+                ("max_poly_x", C.c_int32), ("gc_clamp", C.c_int32), ("max_end_gc", C.c_int32),
+                ("n_size_ranges", C.c_int32), ("size_lo", C.c_int32 * 8), ("size_hi", C.c_int32 * 8)]
+
+
+P3_OLIGO_DTYPE = np.dtype([("seq", OLIGO_DTYPE), ("tm", "<f8"), ("gc_percent", "<f8"), ("penalty", "<f8"),
+                           ("self_any_th", "<f8"), ("self_end_th", "<f8"), ("hairpin_th", "<f8"),
+                           ("start", "<i4"), ("len", "<i4"), ("set", "<i4"), ("flags", "<i4")])
+P3_TASK_DTYPE = np.dtype([("set", "<i4"), ("side", "<i4"), ("start", "<i4"), ("len", "<i4")])
+P3_PAIR_DTYPE = np.dtype([("other", P3_OLIGO_DTYPE), ("pair_penalty", "<f8"), ("compl_any_th", "<f8"),
+                          ("compl_end_th", "<f8"), ("product_size", "<i4"), ("size_range", "<i4")])
+assert P3_OLIGO_DTYPE.itemsize == 80 and P3_PAIR_DTYPE.itemsize == 112 and P3_TASK_DTYPE.itemsize == 16
+P3_OK, P3_SELF_DONE, P3_SELF_FAILED = 1, 2, 4
+
+
 # every symbol include/polyoligo_b200.h declares
 EXPORTS = {
     "po_init": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
@@ -78,6 +103,11 @@ EXPORTS = {
     "po_tm_nn_batch": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "po_annotate_mutations_batch": (C.c_int, [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_void_p,
                                                                                C.c_int, C.c_void_p, C.c_void_p]),
+    "po_p3_candidates_batch": (C.c_int, [C.c_void_p, C.POINTER(P3Settings), C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),
+    "po_p3_design_fixed_batch": (C.c_int, [C.c_void_p, C.POINTER(P3Settings), C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
     "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "po_launch_count": (C.c_int64, [C.c_void_p]),
     "po_thal_count_relaxations": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
@@ -233,6 +263,49 @@ class Context:
                                                      b.ctypes.data if b is not None else None, len(a),
                                                      C.byref(v)), "po_thal_count_relaxations")
         return v.value
+
+    # ---- primer picking (po_p3_*) -------------------------------------------------
+    @staticmethod
+    def _p3_inputs(templates, masks):
+        blob, off = _seq_blob(templates)
+        if masks is None:
+            m = None
+        else:
+            m = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8) for x in masks])
+                                     if len(masks) else np.zeros(0, np.uint8))
+            if m.size != blob.size:
+                raise ValueError("masks and templates differ in length")
+        return np.ascontiguousarray(blob), off, m
+
+    def p3_candidates(self, settings, templates, masks=None):
+        """Sorted candidate lists of every template: (list_off[2*n+1], records)."""
+        blob, off, m = self._p3_inputs(templates, masks)
+        n = len(off) - 1
+        list_off = np.zeros(2 * n + 1, dtype=np.int64)
+        args = (self._h, C.byref(settings), blob.ctypes.data if blob.size else None,
+                m.ctypes.data if m is not None and m.size else None, off.ctypes.data, n, list_off.ctypes.data)
+        self._check(load().po_p3_candidates_batch(*args, None, 0), "po_p3_candidates_batch")
+        out = np.zeros(int(list_off[-1]), dtype=P3_OLIGO_DTYPE)
+        if out.size:
+            self._check(load().po_p3_candidates_batch(*args, out.ctypes.data, out.size), "po_p3_candidates_batch")
+        return list_off, out
+
+    def p3_design_fixed(self, settings, templates, tasks, masks=None, targets=None):
+        """designPrimers with one primer given: (fixed records, pairs[n_tasks, num_return], n_pairs)."""
+        blob, off, m = self._p3_inputs(templates, masks)
+        n = len(off) - 1
+        tasks = np.ascontiguousarray(tasks, dtype=P3_TASK_DTYPE)
+        nt = len(tasks)
+        tg = None if targets is None else np.ascontiguousarray(targets, dtype=np.int32).reshape(n, 2)
+        fixed = np.zeros(nt, dtype=P3_OLIGO_DTYPE)
+        pairs = np.zeros((nt, settings.num_return), dtype=P3_PAIR_DTYPE)
+        n_pairs = np.zeros(nt, dtype=np.int32)
+        self._check(load().po_p3_design_fixed_batch(
+            self._h, C.byref(settings), blob.ctypes.data if blob.size else None,
+            m.ctypes.data if m is not None and m.size else None, off.ctypes.data,
+            tg.ctypes.data if tg is not None else None, n, tasks.ctypes.data, nt, fixed.ctypes.data,
+            pairs.ctypes.data, n_pairs.ctypes.data), "po_p3_design_fixed_batch")
+        return fixed, pairs, n_pairs
 
     # ---- device-pointer calls (torch tensors / raw pointers) --------------------
     def thal_batch_dev(self, type_, d_a, d_b, n, d_out, stream=None):

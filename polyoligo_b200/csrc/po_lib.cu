@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po_thal_out* __restrict__ out,
        const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
        const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
-       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax) {
+       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax, int end_mode) {
     using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem);
@@ -65,7 +65,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
         t = __shfl_sync(FULL, t, 0);
         if (t >= total) break;
         const long long item = list ? list[t] : (long long)t;
-        const uint4 oa = A[item];
+        uint4 oa = A[item];
         // upper bound of the finite-cell count: exact count is cheap from base composition
         if constexpr (HAIRPIN) {
             int a, c, g, t_;
@@ -77,7 +77,12 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
             }
             thal_hairpin_warp<PO_HAIRPIN_GROUP, CAP, COUNT>(*tb, *xt, TA, gt, ws, oa, K, out + item, relax);
         } else {
-            const uint4 ob = B ? B[item] : oa;
+            uint4 ob = B ? B[item] : oa;
+            if (end_mode == 2) {  // thal type END2 is END1 with the oligos swapped (upstream thal())
+                const uint4 tmp = oa;
+                oa = ob;
+                ob = tmp;
+            }
             int a1, c1, g1, t1, a2, c2, g2, t2;
             po_base_counts(oa, po_len(oa), a1, c1, g1, t1);
             po_base_counts(ob, po_len(ob), a2, c2, g2, t2);
@@ -86,7 +91,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                 if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
                 continue;
             }
-            thal_dimer_warp<PO_DIMER_GROUP, CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, out + item, relax);
+            thal_dimer_warp<PO_DIMER_GROUP, CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item, relax);
         }
     }
 }
@@ -197,6 +202,7 @@ struct po_ctx {
     // grow-only device scratch
     DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow;
     DevBuf scratch[12];
+    DevBuf p3[26];  // primer picking (po_p3.cuh)
     unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
     // pinned staging for the host entry points
     DevBuf h_in, h_out;
@@ -289,6 +295,8 @@ extern "C" void po_destroy(po_ctx* ctx) {
         if (b->p) cudaFree(b->p);
     for (DevBuf& sb : ctx->scratch)
         if (sb.p) cudaFree(sb.p);
+    for (DevBuf& sb : ctx->p3)
+        if (sb.p) cudaFree(sb.p);
     if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
@@ -368,7 +376,8 @@ extern "C" int po_unpack(const po_oligo* packed, int64_t n, char* out) {
 template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
 static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4* B, long long n, po_thal_out* out,
                        unsigned long long* work, const long long* list, const unsigned long long* list_n,
-                       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax) {
+                       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax,
+                       int end_mode = 0) {
     using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
     const size_t smem = sizeof(SmemTables) + sizeof(SmemExtra) + WARPS * sizeof(Ws);
     auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN>;
@@ -386,7 +395,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
     }
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, B, n, out, ctx->d_tables, ctx->K, work, list, list_n, overflow,
-                                                     overflow_n, relax);
+                                                     overflow_n, relax, end_mode);
     ctx->launches++;
     CK(cudaGetLastError());
     return PO_OK;
@@ -418,16 +427,17 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
         if (rc) return rc;
         return launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx);
     }
-    if (type != PO_THAL_ANY) {
-        ctx->err = "po_thal: only PO_THAL_ANY and PO_THAL_HAIRPIN are implemented on the device";
+    if (type != PO_THAL_ANY && type != PO_THAL_END1 && type != PO_THAL_END2) {
+        ctx->err = "po_thal: unknown alignment type";
         return PO_E_INVALID;
     }
-    if (cap == 192) rc = launch_thal<192, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
-    else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
-    else rc = launch_thal<256, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+    const int em = type == PO_THAL_END1 ? 1 : type == PO_THAL_END2 ? 2 : 0;
+    if (cap == 192) rc = launch_thal<192, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em);
+    else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em);
+    else rc = launch_thal<256, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em);
     if (rc) return rc;
-    if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx))) return rc;
-    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx);
+    if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em))) return rc;
+    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em);
 }
 
 extern "C" int po_thal_batch_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out,
@@ -878,3 +888,5 @@ extern "C" int po_annotate_mutations_batch(po_ctx* ctx, const int64_t* mut_pos, 
     CK(cudaStreamSynchronize(st));
     return PO_OK;
 }
+
+#include "po_p3.cuh"

@@ -124,8 +124,8 @@ __device__ __forceinline__ void dimer_scan(const Grp<G>& g, const TabAddr& A, co
 
 template <int G, int CAP, bool COUNT>
 __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const TabAddr& A, DimerWs<CAP>& ws,
-                                const uint4 oa, const uint4 ob, const PoConsts& K, po_thal_out* out,
-                                unsigned long long* relax) {
+                                const uint4 oa, const uint4 ob, const PoConsts& K, const bool end_only,
+                                po_thal_out* out, unsigned long long* relax) {
     const int lane = threadIdx.x & 31;
     const Grp<G> g = Grp<G>::make();
     const Grp<32> gw = Grp<32>::make();
@@ -310,9 +310,10 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
     }
 
     // ---- end scan: minimum dG over all cells, first in row-major order wins ---
+    // (thal types END1 / END2: only the cells of the last row, i == len1)
     double bestG = PO_INF;
     int bestK = KEY_NONE;
-    for (int k0 = 0; k0 < ncell; k0 += 32) {
+    for (int k0 = end_only ? ws.start[len1] : 0; k0 < ncell; k0 += 32) {
         const bool act = k0 + lane < ncell;
         const int k = act ? k0 + lane : 0;
         const uint32_t code = ws.code[k];
@@ -326,7 +327,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             bestK = k;
         }
     }
-    if (COUNT) cnt += (lane == 0) ? len1 * len2 : 0;
+    if (COUNT) cnt += (lane == 0) ? (end_only ? len2 : len1 * len2) : 0;
     double wG = PO_INF;
     int wK = KEY_NONE;
     const int gsrc = gw.argmin(bestG, bestK, &wG, &wK);
@@ -335,9 +336,13 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         const unsigned total_cnt = __reduce_add_sync(FULL, (unsigned)cnt);
         if (lane == 0) atomicAdd(relax, (unsigned long long)total_cnt);
     }
-    if (gsrc < 0 || !fin(wG)) {  // no finite cell: no structure, tm = 0
-        if (lane == 0) *out = r;
-        return;
+    if (gsrc < 0 || !fin(wG)) {
+        // upstream falls back to cell (1,1); without a finite value there: no structure, tm = 0
+        if (!(ROWMASK(1) & 1ull)) {
+            if (lane == 0) *out = r;
+            return;
+        }
+        wK = 0;
     }
     int i = CODE_I(ws.code[wK]), j = CODE_J(ws.code[wK]);
     const int bestI = i, bestJ = j;

@@ -1,0 +1,215 @@
+"""Primer picker (designPrimers replacement): GPU path against the
+brute-force CPU oracle (oracle/p3_oracle.py).  libprimer3 itself is absent: parity with the
+real library is unpinned, these tests pin the GPU path to the restated semantics."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from oracle import p3_oracle  # noqa: E402
+
+import polyoligo_b200 as po  # noqa: E402
+from polyoligo_b200 import _native, primer3_bindings as p3b  # noqa: E402
+
+KASP_GLOBALS = {   # reference src/polyoligo/data/PRIMER3_KASP.yaml
+    "PRIMER_OPT_SIZE": 20, "PRIMER_MIN_SIZE": 18, "PRIMER_MAX_SIZE": 25, "PRIMER_OPT_TM": 60.0,
+    "PRIMER_MIN_TM": 55.0, "PRIMER_MAX_TM": 65.0, "PRIMER_MIN_GC": 20.0, "PRIMER_MAX_GC": 80.0,
+    "PRIMER_MAX_POLY_X": 100, "PRIMER_SALT_MONOVALENT": 50.0, "PRIMER_DNA_CONC": 50.0,
+    "PRIMER_MAX_NS_ACCEPTED": 0, "PRIMER_MAX_SELF_ANY": 12, "PRIMER_MAX_SELF_END": 8,
+    "PRIMER_PAIR_MAX_DIFF_TM": 6.0, "PRIMER_PAIR_MAX_COMPL_ANY": 12, "PRIMER_PAIR_MAX_COMPL_END": 8,
+    "PRIMER_PRODUCT_SIZE_RANGE": [[90, 150], [100, 200], [50, 250]], "PRIMER_FIRST_BASE_INDEX": 0,
+    "PRIMER_PICK_INTERNAL_OLIGO": 0, "PRIMER_INTERNAL_MAX_SELF_END": 8, "PRIMER_INTERNAL_MAX_POLY_X": 100,
+}
+
+
+def oracle_settings(g, num_return):
+    return dict(min_size=g["PRIMER_MIN_SIZE"], opt_size=g["PRIMER_OPT_SIZE"], max_size=g["PRIMER_MAX_SIZE"],
+                num_return=num_return, min_tm=g["PRIMER_MIN_TM"], opt_tm=g["PRIMER_OPT_TM"], max_tm=g["PRIMER_MAX_TM"],
+                min_gc=g["PRIMER_MIN_GC"], max_gc=g["PRIMER_MAX_GC"], max_poly_x=g["PRIMER_MAX_POLY_X"],
+                pair_max_diff_tm=g["PRIMER_PAIR_MAX_DIFF_TM"],
+                size_ranges=tuple(tuple(x) for x in g["PRIMER_PRODUCT_SIZE_RANGE"]))
+
+
+def rand_template(rng, n, gc=0.45):
+    p = [(1 - gc) / 2, gc / 2, gc / 2, (1 - gc) / 2]
+    return "".join(np.array(list("ACGT"))[rng.choice(4, n, p=p)])
+
+
+# ---- CPU: host logic ---------------------------------------------------------------------------
+def test_settings_struct_matches_header():
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "polyoligo_b200.h")).read()
+    body = hdr[hdr.index("typedef struct {\n    int32_t min_size, opt_size, max_size;"):hdr.index("} po_p3_settings;")]
+    for name, _ in _native.P3Settings._fields_:
+        assert name in body, name
+    assert C.sizeof(_native.P3Settings) == 248
+
+
+def test_globals_to_settings_and_job_masks():
+    p3b.resetP3Globals()
+    p3b.setP3Globals({**KASP_GLOBALS, "PRIMER_NUM_RETURN": 7})
+    s = p3b.settings_from_globals()
+    assert (s.min_size, s.opt_size, s.max_size, s.num_return) == (18, 20, 25, 7)
+    assert (s.dv_conc, s.dntp_conc) == (1.5, 0.6)           # libprimer3 defaults the YAML does not override
+    assert s.n_size_ranges == 3 and list(s.size_lo[:3]) == [90, 100, 50] and list(s.size_hi[:3]) == [150, 200, 250]
+    with pytest.raises(ValueError):
+        p3b.setP3Globals({"PRIMER_MAX_TEMPLATE_MISPRIMING": 12})
+    t = "ACGT" * 30
+    j = p3b._Job({"SEQUENCE_TEMPLATE": t, "SEQUENCE_EXCLUDED_REGION": [[5, 3], [100, 50]], "SEQUENCE_TARGET": [40, 2],
+                  "SEQUENCE_PRIMER": t[10:30], "SEQUENCE_PRIMER_REVCOMP": p3b._revcomp(t[60:81])})
+    assert j.mask[5:8].all() and j.mask[100:].all() and j.mask[40:42].all() and j.mask.sum() == 3 + 20 + 2
+    assert j.left == (2, 20)            # first occurrence, like strstr
+    assert j.right == (0 + 21 - 1, 21)
+    assert p3b._Job({"SEQUENCE_TEMPLATE": t, "SEQUENCE_PRIMER": "GGGGGGGGGGGGGGGGGGGG"}).error
+    p3b.resetP3Globals()
+
+
+def test_oracle_design_properties(oracle):
+    rng = np.random.default_rng(3)
+    t = rand_template(rng, 160)
+    s = oracle_settings(KASP_GLOBALS, 6)
+    s["size_ranges"] = ((60, 90), (50, 140))
+    res = p3_oracle.design(oracle, s, t, excluded=[(0, 5)], nthreads=4)
+    assert 0 < len(res) <= 6
+    keys = [(r["size_range"], r["pair_penalty"]) for r in res]
+    assert keys == sorted(keys)
+    seen = set()
+    for r in res:
+        l, rr = r["left"], r["right"]
+        assert t[l["start"]:l["start"] + l["len"]] == l["seq"]
+        assert p3b._revcomp(t[rr["start"] - rr["len"] + 1:rr["start"] + 1]) == rr["seq"]
+        assert r["product_size"] == rr["start"] - l["start"] + 1
+        lo, hi = s["size_ranges"][r["size_range"]]
+        assert lo <= r["product_size"] <= hi and l["start"] >= 5
+        assert abs(l["tm"] - rr["tm"]) <= 6.0 and r["pair_penalty"] == l["penalty"] + rr["penalty"]
+        assert (l["start"], l["len"], rr["start"], rr["len"]) not in seen
+        seen.add((l["start"], l["len"], rr["start"], rr["len"]))
+
+
+# ---- GPU: parity with the oracle ----------------------------------------------------------------
+def _gpu_settings(num_return):
+    p3b.resetP3Globals()
+    p3b.setP3Globals({**KASP_GLOBALS, "PRIMER_NUM_RETURN": num_return})
+    return p3b.settings_from_globals()
+
+
+def _same_oligo(rec, seq, ref):
+    assert seq == ref["seq"]
+    assert (int(rec["start"]), int(rec["len"])) == (ref["start"], ref["len"])
+    for f in ("tm", "gc_percent", "penalty"):
+        assert float(rec[f]) == ref[f], f
+
+
+@pytest.mark.gpu
+def test_candidate_lists_match_oracle(ctx):
+    rng = np.random.default_rng(8)
+    templates = [rand_template(rng, n) for n in (140, 90, 30, 17, 200)]
+    templates[1] = templates[1][:40] + "N" + templates[1][41:]
+    masks = [np.zeros(len(t), np.uint8) for t in templates]
+    masks[0][50:70] = 1
+    masks[4][:3] = 1
+    s = _gpu_settings(5)
+    list_off, recs = ctx.p3_candidates(s, templates, masks)
+    seqs = _native.unpack(recs["seq"])
+    so = oracle_settings(KASP_GLOBALS, 5)
+    so = {**p3_oracle.DEFAULTS, **so}
+    total = 0
+    for k, (t, m) in enumerate(zip(templates, masks)):
+        for strand, side in enumerate("LR"):
+            ref = p3_oracle.candidates(so, t, list(m), side)
+            lo, hi = list_off[2 * k + strand], list_off[2 * k + strand + 1]
+            assert hi - lo == len(ref), (k, side)
+            for i, r in enumerate(ref):
+                _same_oligo(recs[lo + i], seqs[lo + i], r)
+                assert recs[lo + i]["set"] == k
+            total += len(ref)
+    assert total > 200
+
+
+def _check_pairs(rows, ref, what):
+    assert len(rows) == len(ref), what
+    for (l, lseq, r, rseq, pq, ca, ce, size, rng_), e in zip(rows, ref):
+        _same_oligo(l, lseq, e["left"])
+        _same_oligo(r, rseq, e["right"])
+        assert float(pq) == e["pair_penalty"] and int(size) == e["product_size"] and int(rng_) == e["size_range"], what
+        assert float(ca) == e["compl_any_th"] and float(ce) == e["compl_end_th"], what
+        for rec, o in ((l, e["left"]), (r, e["right"])):
+            for f in ("self_any_th", "self_end_th", "hairpin_th"):
+                assert float(rec[f]) == o[f], (what, f)
+
+
+@pytest.mark.gpu
+def test_fixed_primer_design_matches_oracle(ctx, oracle):
+    rng = np.random.default_rng(12)
+    s = _gpu_settings(12)
+    so = oracle_settings(KASP_GLOBALS, 12)
+    templates = [rand_template(rng, 320), rand_template(rng, 260, gc=0.5)]
+    masks = [np.zeros(len(t), np.uint8) for t in templates]
+    masks[0][200:215] = 1
+    tasks, refs = [], []
+    for k, t in enumerate(templates):
+        full = {**p3_oracle.DEFAULTS, **so}
+        lefts = [r for r in p3_oracle.candidates(full, t, list(masks[k]), "L") if 100 <= r["start"] <= 140][:3]
+        rights = [r for r in p3_oracle.candidates(full, t, list(masks[k]), "R") if 150 <= r["start"] <= 190][:3]
+        excluded = [(200, 15)] if k == 0 else []
+        for r in lefts:
+            tasks.append((k, 1, r["start"], r["len"]))
+            refs.append(p3_oracle.design(oracle, so, t, excluded=excluded, left=r["seq"]))
+        for r in rights:
+            tasks.append((k, 2, r["start"], r["len"]))
+            refs.append(p3_oracle.design(oracle, so, t, excluded=excluded, right=r["seq"]))
+        # a given primer that violates the Tm limits yields nothing
+        tasks.append((k, 1, 5, 18))
+        refs.append(p3_oracle.design(oracle, so, t, excluded=excluded, left=t[5:23]))
+    tasks = np.array(tasks, dtype=_native.P3_TASK_DTYPE)
+    fixed, pairs, n_pairs = ctx.p3_design_fixed(s, templates, tasks, masks)
+    assert sum(len(r) for r in refs) > 60
+    for t in range(len(tasks)):
+        n = int(n_pairs[t])
+        others = pairs[t, :n]["other"]
+        oseq = _native.unpack(others["seq"]) if n else []
+        fseq = _native.unpack(fixed[t:t + 1]["seq"])[0]
+        rows = []
+        for i in range(n):
+            p = pairs[t, i]
+            if tasks[t]["side"] == 1:
+                rows.append((fixed[t], fseq, others[i], oseq[i], p["pair_penalty"], p["compl_any_th"],
+                             p["compl_end_th"], p["product_size"], p["size_range"]))
+            else:
+                rows.append((others[i], oseq[i], fixed[t], fseq, p["pair_penalty"], p["compl_any_th"],
+                             p["compl_end_th"], p["product_size"], p["size_range"]))
+        _check_pairs(rows, refs[t], "task %d" % t)
+
+
+@pytest.mark.gpu
+def test_design_primers_dict_matches_oracle(ctx, oracle):
+    rng = np.random.default_rng(5)
+    t = rand_template(rng, 170)
+    g = {**KASP_GLOBALS, "PRIMER_NUM_RETURN": 8, "PRIMER_PRODUCT_SIZE_RANGE": [[70, 100], [60, 150]]}
+    p3b.resetP3Globals()
+    p3b.setP3Globals(g)
+    so = oracle_settings(g, 8)
+    # both primers picked, with a target and an excluded region (the PCR / HRM / CAPS call shape)
+    res = p3b.designPrimers({"SEQUENCE_TEMPLATE": t, "SEQUENCE_TARGET": [80, 4], "SEQUENCE_EXCLUDED_REGION": [[0, 8]]})
+    ref = p3_oracle.design(oracle, so, t, excluded=[(0, 8)], target=(80, 4))
+    assert res["PRIMER_PAIR_NUM_RETURNED"] == len(ref) > 0
+    for i, e in enumerate(ref):
+        assert res["PRIMER_LEFT_%d_SEQUENCE" % i] == e["left"]["seq"]
+        assert res["PRIMER_RIGHT_%d_SEQUENCE" % i] == e["right"]["seq"]
+        assert res["PRIMER_LEFT_%d" % i] == (e["left"]["start"], e["left"]["len"])
+        assert res["PRIMER_RIGHT_%d" % i] == (e["right"]["start"], e["right"]["len"])
+        assert res["PRIMER_PAIR_%d_PENALTY" % i] == e["pair_penalty"]
+        assert res["PRIMER_PAIR_%d_COMPL_ANY_TH" % i] == e["compl_any_th"]
+        assert res["PRIMER_PAIR_%d_COMPL_END_TH" % i] == e["compl_end_th"]
+        assert res["PRIMER_PAIR_%d_PRODUCT_SIZE" % i] == e["product_size"]
+        assert res["PRIMER_LEFT_%d_TM" % i] == e["left"]["tm"] and res["PRIMER_RIGHT_%d_HAIRPIN_TH" % i] == e["right"]["hairpin_th"]
+    # the KASP call shape through the same entry point
+    left = ref[0]["left"]["seq"]
+    res = p3b.designPrimers({"SEQUENCE_TEMPLATE": t, "SEQUENCE_PRIMER": left})
+    ref2 = p3_oracle.design(oracle, so, t, left=left)
+    assert res["PRIMER_PAIR_NUM_RETURNED"] == len(ref2) > 0
+    assert [res["PRIMER_RIGHT_%d_SEQUENCE" % i] for i in range(len(ref2))] == [e["right"]["seq"] for e in ref2]
+    assert p3b.designPrimers({"SEQUENCE_TEMPLATE": t, "SEQUENCE_PRIMER": "ACGTACGTACGTACGTACGTAA"}).get("PRIMER_ERROR")
+    p3b.resetP3Globals()

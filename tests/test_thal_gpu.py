@@ -55,6 +55,23 @@ def test_adversarial_inputs(ctx, oracle):
     assert_parity(ctx.thal_batch(po.THAL_HAIRPIN, pb), oracle.thal_batch(b, None, 4, nthreads=8), "adversarial hairpin b")
 
 
+def test_end_anchored_types(ctx, oracle):
+    # thal END1 / END2 (3'-anchored): what primer3's self_end_th / compl_end_th are built from
+    a, b = config4_pairs(6000, seed=21)
+    rng = np.random.default_rng(17)
+    x, y = adversarial_pairs(rng)
+    a, b = a + x, b + y
+    pa, pb = po.pack(a), po.pack(b)
+    for t in (po.THAL_END1, po.THAL_END2):
+        got = ctx.thal_batch(t, pa, pb)
+        ref = oracle.thal_batch(a, b, t, nthreads=8)
+        assert_parity(got, ref, "end type %d" % t)
+        found = ref["structure_found"] == 1
+        assert np.array_equal(got["align_end_1"][found], ref["align_end_1"][found])
+        assert np.array_equal(got["align_end_2"][found], ref["align_end_2"][found])
+    assert_parity(ctx.thal_batch(po.THAL_END1, pa), oracle.thal_batch(a, a, 2, nthreads=8), "self end")
+
+
 def test_kasp_tailed_shape(ctx, oracle):
     # reporter + allele-specific primer against the common primer (reference _lib_kasp.py:95-105)
     rng = np.random.default_rng(5)
