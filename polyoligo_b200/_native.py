@@ -270,6 +270,8 @@ class Context:
         blob, off = _seq_blob(templates)
         if masks is None:
             m = None
+        elif isinstance(masks, np.ndarray) and masks.dtype == np.uint8 and masks.size == blob.size:
+            m = np.ascontiguousarray(masks).reshape(-1)     # already concatenated
         else:
             m = np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint8) for x in masks])
                                      if len(masks) else np.zeros(0, np.uint8))

@@ -7,6 +7,8 @@ candidates with the CUDA enumeration kernel, scores all of them with one
 oligo-properties pass and keeps, per marker and in the reference's order, the
 slots whose REF and ALT primers are both valid.
 """
+from copy import deepcopy
+
 import numpy as np
 
 from . import _native, lib_primer3
@@ -143,3 +145,123 @@ def get_marker_primers_batch(hrois, device=None, return_all=False):
 
 def get_marker_primers(hroi, device=None):
     return get_marker_primers_batch([hroi], device)[0]
+
+
+def merge_primers(mpp, p3_primers):
+    """reference _lib_kasp.py:552-566: one PrimerPair per primer3 pair, the marker primer pair
+    completed with the picked common primer; the ALT primer takes the marker primer's coordinates."""
+    pps = []
+    for pp3 in p3_primers:
+        pp = deepcopy(mpp)
+        pp.add_primer3_attributes(pp3)
+        pp.primers["A"].start = pp.primers[pp.dir].start
+        pp.primers["A"].stop = pp.primers[pp.dir].stop
+        pp.primers["A"].id = pp.primers[pp.dir].id
+        pps.append(pp)
+    return pps
+
+
+def design_primers_multi(jobs, n_primers=10, device=None):
+    """design_primers (reference _lib_kasp.py:568-631) for many markers: ``jobs`` is a list of
+    dicts(pps_repo, mpps, roi, sequence_target=None, sequence_excluded_region=None).  Every
+    designPrimers call of every marker goes to the GPU in one batch, the validity of every
+    picked common primer is evaluated in one batch, and the round-robin merge then makes the
+    reference's decisions in the reference's order."""
+    seq_args, starts, owner = [], [], []
+    for j, job in enumerate(jobs):
+        roi = job["roi"]
+        base = {"SEQUENCE_TEMPLATE": roi.seq}
+        if job.get("sequence_target") is not None:
+            base["SEQUENCE_TARGET"] = job["sequence_target"]
+        if job.get("sequence_excluded_region") is not None:
+            base["SEQUENCE_EXCLUDED_REGION"] = job["sequence_excluded_region"]
+        for mpp in job["mpps"]:
+            args = dict(base)
+            key = "SEQUENCE_PRIMER" if mpp.dir == "F" else "SEQUENCE_PRIMER_REVCOMP"
+            args[key] = mpp.primers[mpp.dir].sequence
+            seq_args.append(args)
+            starts.append(roi.start)
+            owner.append(j)
+    p3_lists = lib_primer3.get_primers_batch(seq_args, starts, device) if seq_args else []
+    repos = [{} for _ in jobs]
+    k = 0
+    for j, job in enumerate(jobs):
+        for pid, mpp in enumerate(job["mpps"]):
+            repos[j][pid] = merge_primers(mpp, p3_lists[k])
+            k += 1
+    # Primer.is_valid of every picked common primer (:621-625), once per distinct sequence
+    commons = [pp.primers["R" if pp.dir == "F" else "F"] for repo in repos for lst in repo.values() for pp in lst]
+    by_seq = {}
+    for p in commons:
+        by_seq.setdefault(p.sequence, lib_primer3.Primer(sequence=p.sequence))
+    uniq = list(by_seq.values())
+    ok = dict(zip(by_seq.keys(), lib_primer3.is_valid_batch(uniq, device))) if uniq else {}
+    for p in commons:
+        src = by_seq[p.sequence]
+        for a in ("length", "gc_content", "nN", "tm", "hairpin_tm", "homodimer_tm"):
+            setattr(p, a, getattr(src, a))
+    out = []
+    for job, p3_repo in zip(jobs, repos):
+        pps_repo = job["pps_repo"]
+        flag_continue = True
+        while flag_continue:
+            for mpp_id in [m for m in p3_repo if len(p3_repo[m]) == 0]:
+                del p3_repo[mpp_id]
+            if len(p3_repo) == 0:
+                flag_continue = False
+            for mpp_id, p3_pps in p3_repo.items():
+                pp = p3_pps.pop(0)
+                is_new = not any(all(rpp.primers[d].sequence == pp.primers[d].sequence for d in "FRA")
+                                 for rpp in pps_repo)
+                if is_new:
+                    common = pp.primers["R" if pp.dir == "F" else "F"]
+                    if ok[common.sequence]:
+                        pps_repo.append(pp)
+                    if len(pps_repo) == n_primers:
+                        flag_continue = False
+                        break
+        out.append(pps_repo)
+    return out
+
+
+def design_primers(pps_repo, mpps, roi, sequence_target=None, sequence_excluded_region=None, n_primers=10,
+                   device=None):
+    return design_primers_multi([dict(pps_repo=pps_repo, mpps=mpps, roi=roi, sequence_target=sequence_target,
+                                      sequence_excluded_region=sequence_excluded_region)], n_primers, device)[0]
+
+
+SEARCH_TYPES_VCF = ["mism_mut", "mism", "partial_mism_mut", "partial_mism", "all_mut", "all"]
+SEARCH_TYPES = ["mism", "partial_mism", "all"]
+
+
+def design_markers(hrois, n_primers=10, reporters=None, device=None):
+    """The design part of _lib_kasp.main (reference _lib_kasp.py:671-743) for many homolog-mapped
+    ROIs at once, with the BLAST off-target search left out (no off-targets).  Each hroi carries
+    seq / start / stop / marker / chrom, p3_sequence_included_maps, mutations and vcf_hook like the
+    reference's lib_markers.ROI after map_homologs + upload_mutations.  Returns one PCR per marker,
+    classified and pruned."""
+    depth = lib_primer3.PRIMER3_GLOBALS["PRIMER_NUM_RETURN"]
+    for hroi in hrois:
+        lib_primer3.include_mut_in_included_maps(hroi)
+        lib_primer3.open_marker_window(hroi)
+        lib_primer3.get_sequence_excluded_regions(hroi)
+    mpps_all = get_marker_primers_batch(hrois, device)
+    pcrs = [PCR(snp_id=h.marker.name if hasattr(h.marker, "name") else None, chrom=getattr(h, "chrom", None),
+                pos=h.marker.pos1, ref=h.marker.ref, alt=h.marker.alt) for h in hrois]
+    n_types = max(len(h.p3_sequence_included_maps) for h in hrois) if hrois else 0
+    for step in range(n_types):
+        jobs, who = [], []
+        for m, (hroi, pcr) in enumerate(zip(hrois, pcrs)):
+            types_ = SEARCH_TYPES_VCF if "mism_mut" in hroi.p3_sequence_included_maps else SEARCH_TYPES
+            if step < len(types_) and len(pcr.pps) < depth:
+                jobs.append(dict(pps_repo=pcr.pps, mpps=mpps_all[m], roi=hroi,
+                                 sequence_excluded_region=hroi.p3_sequence_excluded_regions[types_[step]]))
+                who.append(m)
+        if jobs:
+            for m, repo in zip(who, design_primers_multi(jobs, n_primers=depth, device=device)):
+                pcrs[m].pps = repo
+    for pcr in pcrs:
+        pcr.add_reporter_dyes(reporters or ("", ""))
+    lib_primer3.add_mutations_batch(pcrs, [list(h.mutations) for h in hrois], device)
+    lib_primer3.rank_batch(pcrs, n_primers, "KASP", device, reporters=reporters)
+    return pcrs

@@ -5,14 +5,15 @@ Same names, attributes and decisions as the reference's ``Primer`` /
 helpers (:564-600), but every thermodynamic quantity comes from BATCHED calls
 into the CUDA library: ``calc_thermals_batch`` evaluates any number of primers
 in one go, and the per-object methods are thin wrappers over batches of one so
-existing callers keep working.  BLAST off-target search (check_offtargeting)
-and primer3's designPrimers stay the reference's external glue and are not here.
+existing callers keep working.  ``get_primers`` (:466-529) goes through
+``primer3_bindings`` (the GPU primer picker).  BLAST off-target search
+(check_offtargeting) stays the reference's external glue and is not here.
 """
 from copy import deepcopy
 
 import numpy as np
 
-from . import _native, lib_utils, scoring
+from . import _native, lib_utils, primer3_bindings, scoring
 from .thermoanalysis import get_context, gc_content
 
 PRIMER3_GLOBALS = {}     # the PRIMER_* thresholds of the assay YAML (reference data/PRIMER3_*.yaml)
@@ -20,7 +21,9 @@ TM_DELTA = 5             # reference lib_primer3.py:21
 
 
 def set_globals(**kwargs):
+    """reference lib_primer3.py:539-544: remembers the tags and hands them to the primer picker."""
     PRIMER3_GLOBALS.update(kwargs)
+    primer3_bindings.setP3Globals(PRIMER3_GLOBALS)
 
 
 def set_tm_delta(v):
@@ -53,6 +56,12 @@ class Primer:
         self.nN = 0
         self.sequence = None
         self.reporter = ""
+        # attributes shared with the primer picker (reference lib_primer3.py:45-51)
+        self.end_stability = None
+        self.hairpin_th = None
+        self.penalty = None
+        self.self_any_th = None
+        self.self_end_th = None
         for k, v in kwargs.items():
             if k in self.__dict__:
                 setattr(self, k, deepcopy(v))
@@ -62,6 +71,12 @@ class Primer:
 
     def is_valid(self):
         return bool(is_valid_batch([self])[0])
+
+    def add_primer3_attributes(self, p3):
+        """reference lib_primer3.py:99-108"""
+        for k in ("id", "start", "stop", "sequence", "end_stability", "hairpin_th", "penalty", "self_any_th",
+                  "self_end_th"):
+            setattr(self, k, getattr(p3, k))
 
 
 def calc_thermals_batch(primers, device=None):
@@ -118,9 +133,20 @@ class PrimerPair:
         self.goodness = None
         self.qcode = None
         self.hrm = None
+        self.compl_any_th = None
+        self.compl_end_th = None
         self.product_size = None
         self.penalty = None
         self.dir = None
+
+    def add_primer3_attributes(self, pp3):
+        """reference lib_primer3.py:139-145"""
+        for d in ("F", "R"):
+            self.primers[d].add_primer3_attributes(pp3.primers[d])
+        self.compl_any_th = pp3.compl_any_th
+        self.compl_end_th = pp3.compl_end_th
+        self.product_size = pp3.product_size
+        self.penalty = pp3.penalty
 
     def check_heterodimerization(self):
         check_heterodimerization_batch([self])
@@ -311,3 +337,61 @@ def hrm_temps_batch(ref_products, alt_products, device=None):
         out.append({"ref": lib_utils.round_tidy(r, 4), "alt": lib_utils.round_tidy(a, 4),
                     "delta": lib_utils.round_tidy(np.abs(r - a), 2)})
     return out
+
+
+def parse_p3_result(p3_primers, target_start=1):
+    """The dict -> [PrimerPair] part of get_primers (reference lib_primer3.py:481-529): pairs in
+    primer-pair-id order, coordinates shifted by target_start, every PRIMER_{LEFT,RIGHT,PAIR}_i_*
+    field except *_TM stored under its lower-cased name."""
+    pps = {}
+    for k, v in p3_primers.items():
+        if k in ("PRIMER_WARNING", "PRIMER_ERROR"):
+            return []          # the whole design run is void
+        fields = k.split("_")
+        try:
+            pid = int(fields[2])
+        except (ValueError, IndexError):
+            continue
+        name = "_".join(fields[3:]).lower()
+        if name == "tm":
+            continue
+        if pid not in pps:
+            pps[pid] = PrimerPair()
+            for d in ("F", "R"):
+                pps[pid].primers[d].id = pid
+        pp = pps[pid]
+        if fields[1] == "LEFT":
+            if name:
+                pp.primers["F"].__dict__[name] = v
+            else:
+                pp.primers["F"].start = target_start + v[0]
+                pp.primers["F"].stop = pp.primers["F"].start + (v[1] - 1)
+        elif fields[1] == "RIGHT":
+            if name:
+                pp.primers["R"].__dict__[name] = v
+            else:
+                pp.primers["R"].stop = target_start + v[0]
+                pp.primers["R"].start = pp.primers["R"].stop - (v[1] - 1)
+        elif fields[1] == "PAIR":
+            pp.__dict__[name] = v
+    return [pps[i] for i in sorted(pps)]
+
+
+def get_primers_batch(seq_args_list, target_starts, device=None):
+    """get_primers (reference lib_primer3.py:466-529) for many designPrimers calls at once."""
+    prepared = []
+    for args in seq_args_list:
+        args = dict(args)
+        for k, v in PRIMER3_GLOBALS.items():
+            if k.startswith("SEQUENCE") and k not in args:
+                args[k] = v
+        for k in ("SEQUENCE_EXCLUDED_REGION", "SEQUENCE_INCLUDED_REGION"):
+            if k in args:
+                args[k] = lib_utils.reduce_ivs(args[k], n=200)   # primer3 refuses more than 200 intervals
+        prepared.append(args)
+    results = primer3_bindings.design_primers_batch(prepared, device=device)
+    return [parse_p3_result(r, ts) for r, ts in zip(results, target_starts)]
+
+
+def get_primers(primer3_seq_args, target_start=1):
+    return get_primers_batch([primer3_seq_args], [target_start])[0]

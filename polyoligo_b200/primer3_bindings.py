@@ -163,10 +163,30 @@ def _p3_context(settings, device=None):
     return ctx
 
 
+# SantaLucia 1998 nearest-neighbour -dG37 in cal/mol (oligotm.c oligodg(), tm_method santalucia)
+_NN_DG = {"AA": 1000, "AC": 1440, "AG": 1280, "AT": 880, "CA": 1450, "CC": 1840, "CG": 2170, "CT": 1280,
+          "GA": 1300, "GC": 2240, "GG": 1840, "GT": 1440, "TA": 580, "TC": 1300, "TG": 1450, "TT": 1000}
+
+
+def end_stability(seq):
+    """libprimer3 end_oligodg(seq, 5): duplex-disruption dG (kcal/mol) of the last five 3' bases.
+    primer3's manual pins the scale: GCGCG = 6.86, TATAT = 0.86."""
+    s = seq[-5:].upper()
+    if len(s) < 2:
+        return 0.0
+    dg = -1960                                   # initiation
+    dg += sum(-50 for c in (s[0], s[-1]) if c in "AT")   # terminal AT penalty
+    dg += sum(_NN_DG[s[k:k + 2]] for k in range(len(s) - 1))
+    if len(s) % 2 == 0 and s == _revcomp(s):
+        dg += -430                               # symmetry correction
+    return dg / 1000.0
+
+
 def _oligo_fields(side, i, rec, seq):
     p = "PRIMER_%s_%d" % (side, i)
     return {p: (int(rec["start"]), int(rec["len"])), p + "_SEQUENCE": seq, p + "_PENALTY": float(rec["penalty"]),
             p + "_TM": float(rec["tm"]), p + "_GC_PERCENT": float(rec["gc_percent"]),
+            p + "_END_STABILITY": end_stability(seq),
             p + "_SELF_ANY_TH": float(rec["self_any_th"]), p + "_SELF_END_TH": float(rec["self_end_th"]),
             p + "_HAIRPIN_TH": float(rec["hairpin_th"])}
 

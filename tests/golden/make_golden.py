@@ -277,7 +277,114 @@ def golden_mutations(rng):
     dump("mutations.json", {"cases": cases})
 
 
+def _p3_dict(pairs):
+    """primer3-py style result dict (key order as primer3 emits it) from oracle picker pairs."""
+    d = {"PRIMER_LEFT_EXPLAIN": "considered 0", "PRIMER_RIGHT_EXPLAIN": "considered 0",
+         "PRIMER_PAIR_EXPLAIN": "considered 0", "PRIMER_LEFT_NUM_RETURNED": len(pairs),
+         "PRIMER_RIGHT_NUM_RETURNED": len(pairs), "PRIMER_INTERNAL_NUM_RETURNED": 0,
+         "PRIMER_PAIR_NUM_RETURNED": len(pairs)}
+    for i, e in enumerate(pairs):
+        d["PRIMER_PAIR_%d_PENALTY" % i] = e["pair_penalty"]
+        for side, o in (("LEFT", e["left"]), ("RIGHT", e["right"])):
+            d["PRIMER_%s_%d_PENALTY" % (side, i)] = o["penalty"]
+        for side, o in (("LEFT", e["left"]), ("RIGHT", e["right"])):
+            d["PRIMER_%s_%d_SEQUENCE" % (side, i)] = o["seq"]
+        for side, o in (("LEFT", e["left"]), ("RIGHT", e["right"])):
+            d["PRIMER_%s_%d" % (side, i)] = [o["start"], o["len"]]
+        for f, k in (("TM", "tm"), ("GC_PERCENT", "gc_percent"), ("SELF_ANY_TH", "self_any_th"),
+                     ("SELF_END_TH", "self_end_th"), ("HAIRPIN_TH", "hairpin_th")):
+            for side, o in (("LEFT", e["left"]), ("RIGHT", e["right"])):
+                d["PRIMER_%s_%d_%s" % (side, i, f)] = o[k]
+        for side, o in (("LEFT", e["left"]), ("RIGHT", e["right"])):
+            d["PRIMER_%s_%d_END_STABILITY" % (side, i)] = 3.21 + 0.01 * i
+        d["PRIMER_PAIR_%d_COMPL_ANY_TH" % i] = e["compl_any_th"]
+        d["PRIMER_PAIR_%d_COMPL_END_TH" % i] = e["compl_end_th"]
+        d["PRIMER_PAIR_%d_PRODUCT_SIZE" % i] = e["product_size"]
+    return d
+
+
+def _pp_row(pp):
+    row = {"dir": pp.dir, "penalty": pp.penalty, "product_size": pp.product_size,
+           "compl_any_th": pp.compl_any_th, "compl_end_th": pp.compl_end_th}
+    for d, p in pp.primers.items():
+        row[d] = {"sequence": p.sequence, "start": p.start, "stop": p.stop, "id": p.id, "penalty": p.penalty,
+                  "end_stability": p.end_stability, "hairpin_th": p.hairpin_th, "self_any_th": p.self_any_th,
+                  "self_end_th": p.self_end_th}
+    return row
+
+
+def golden_design(rng):
+    """a5 (result parsing), a6 and a7: the reference's get_primers / KASP design_primers + merge_primers
+    (_lib_kasp.py:552-631) / PCR design_primers (_lib_pcr.py:167-219) run on CANNED designPrimers
+    answers (made by the picker oracle; primer3 itself is not installable), so the selection logic
+    around the picker is pinned to the reference's own code."""
+    from oracle import p3_oracle
+    import polyoligo._lib_pcr as lpcr
+    oracle = Oracle()
+    lp.set_tm_delta(5.0)
+    lp.PRIMER3_GLOBALS.clear()
+    lp.PRIMER3_GLOBALS.update(KASP_GLOBALS)
+    so = dict(min_size=18, opt_size=20, max_size=25, num_return=6, min_tm=55.0, opt_tm=60.0, max_tm=65.0,
+              min_gc=20.0, max_gc=80.0, max_poly_x=100, pair_max_diff_tm=6.0,
+              size_ranges=((90, 150), (100, 200), (50, 250)),
+              # same salt as ThermoAnalysis() so that many picked primers also pass Primer.is_valid
+              # and the merge logic is exercised; what the picker answers is canned either way
+              dv_conc=0.0, dntp_conc=0.0)
+    canned = []
+
+    def fake_design(seq_args):
+        excluded = [tuple(x) for x in seq_args.get("SEQUENCE_EXCLUDED_REGION", [])]
+        tgt = seq_args.get("SEQUENCE_TARGET")
+        res = p3_oracle.design(oracle, so, seq_args["SEQUENCE_TEMPLATE"], excluded=excluded,
+                               target=tuple(tgt) if tgt else None, left=seq_args.get("SEQUENCE_PRIMER"),
+                               right=seq_args.get("SEQUENCE_PRIMER_REVCOMP"))
+        d = _p3_dict(res)
+        canned.append(list(d.items()))
+        return d
+
+    sys.modules["primer3"].bindings.designPrimers = fake_design
+    kasp_cases = []
+    for _ in range(2):
+        seq = rand_seq(rng, 400, gc=0.48)
+        start = int(rng.integers(1000, 100000))
+        idx = 199
+        ref = seq[idx]
+        alt = rand_seq(rng, 1)
+        while alt == ref:
+            alt = rand_seq(rng, 1)
+        hroi = make_hroi(seq, start, start + idx, ref, alt)
+        mpps = lk.get_marker_primers(hroi)
+        del canned[:]
+        excluded = [[0, 12], [300, 25]]
+        repo = lk.design_primers(pps_repo=[], mpps=mpps, roi=hroi, sequence_excluded_region=excluded, n_primers=10)
+        first = [_pp_row(pp) for pp in repo]
+        # second search pass into the same repository (as _lib_kasp.main does per search type)
+        n1 = len(canned)
+        repo = lk.design_primers(pps_repo=repo, mpps=mpps, roi=hroi, sequence_excluded_region=[[0, 5]],
+                                 n_primers=14)
+        kasp_cases.append({"seq": seq, "start": start, "stop": hroi.stop, "pos1": hroi.marker.pos1, "ref": ref,
+                           "alt": alt, "excluded": [excluded, [[0, 5]]], "n_primers": [10, 14],
+                           "canned": [canned[:n1], canned[n1:]], "repo": [first, [_pp_row(pp) for pp in repo]]})
+    # PCR: both primers picked, diversity limit max_unique = 2
+    pcr_cases = []
+    for _ in range(2):
+        seq = rand_seq(rng, 220, gc=0.5)
+        roi = types.SimpleNamespace(seq=seq, chrom="chrP", left_roi=types.SimpleNamespace(start=5000))
+        del canned[:]
+        so["num_return"] = 30
+        so["size_ranges"] = ((80, 160),)
+        repo = lpcr.design_primers(pps_repo=[], roi=roi, sequence_target=[100, 6],
+                                   sequence_excluded_region=[[0, 4]], n_primers=8, max_unique=2)
+        pcr_cases.append({"seq": seq, "left_start": 5000, "target": [100, 6], "excluded": [[0, 4]], "n_primers": 8,
+                          "max_unique": 2, "canned": canned[0], "repo": [_pp_row(pp) for pp in repo]})
+    sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
+    dump("design.json", {"globals": KASP_GLOBALS, "tm_delta": 5.0, "kasp": kasp_cases, "pcr": pcr_cases})
+
+
 if __name__ == "__main__":
+    if "--design-only" in sys.argv:
+        golden_design(np.random.default_rng(20240610))
+        sys.exit(0)
     rng = np.random.default_rng(20240608)
     golden_marker_primers(rng)
     golden_is_valid(rng)
@@ -285,3 +392,4 @@ if __name__ == "__main__":
     golden_scoring(rng)
     golden_masks(rng)
     golden_mutations(np.random.default_rng(20240609))
+    golden_design(np.random.default_rng(20240610))
