@@ -44,6 +44,8 @@ def parse():
     p.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
     p.add_argument("--cpu-sample", type=int, default=150_000, help="pairs in the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--markers", type=int, default=2048,
+                   help="markers per GPU of the secondary config-5 (KASP design) measurement; 0 skips it")
     return p.parse_args()
 
 
@@ -137,6 +139,42 @@ class ClockSampler(threading.Thread):
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_config5(args, rank, local_rank, barrier):
+    """BASELINE config 5: the whole KASP design (enumeration, validity, common-primer picking,
+    merge, reporter-tailed heterodimers, goodness, top-10) of synthetic markers through the public
+    array API with HOST buffers; wall clock of one pass after a small warm-up."""
+    from polyoligo_b200 import kasp_pipeline as kp, lib_primer3 as lp, primer3_bindings as p3b
+    from polyoligo_b200.thermoanalysis import get_context
+    p3b.resetP3Globals()
+    lp.PRIMER3_GLOBALS.clear()
+    # reference src/polyoligo/data/PRIMER3_KASP.yaml + cli_kasp.py defaults (--depth 100, -n 10, dyes)
+    lp.set_globals(PRIMER_OPT_SIZE=20, PRIMER_MIN_SIZE=18, PRIMER_MAX_SIZE=25, PRIMER_OPT_TM=60.0,
+                   PRIMER_MIN_TM=55.0, PRIMER_MAX_TM=65.0, PRIMER_MIN_GC=20.0, PRIMER_MAX_GC=80.0,
+                   PRIMER_MAX_POLY_X=100, PRIMER_SALT_MONOVALENT=50.0, PRIMER_DNA_CONC=50.0,
+                   PRIMER_MAX_NS_ACCEPTED=0, PRIMER_PAIR_MAX_DIFF_TM=6.0,
+                   PRIMER_PRODUCT_SIZE_RANGE=[[90, 150], [100, 200], [50, 250]], PRIMER_NUM_RETURN=100)
+    lp.set_tm_delta(5.0)
+    dyes = ("GAAGGTCGGAGTCAACGGATT", "GAAGGTGACCAAGTTCATGCT")
+    kctx = get_context(local_rank)
+    kp.design_markers_arrays(kp.synth_config5(128, seed=1), n_primers=10, reporters=dyes, device=local_rank)
+    data = kp.synth_config5(args.markers, seed=kp.CONFIG5_SEED + rank)
+    stats = {}
+    items0, launches0 = kctx.thal_item_count(), kctx.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    res = kp.design_markers_arrays(data, n_primers=10, reporters=dyes, device=local_rank, stats=stats)
+    dt = time.perf_counter() - t0
+    barrier()
+    c5 = {"workload": "synthetic KASP design, %d markers per GPU x 500 nt, SNP at 249, depth 100, top 10, "
+                      "no off-targets (BASELINE config 5 shape)" % args.markers,
+          "timing": "host wall clock of one pass through kasp_pipeline.design_markers_arrays (host buffers)",
+          "thal_evaluations_rank0": int(kctx.thal_item_count() - items0),
+          "gpu_launches": int(kctx.launch_count() - launches0),
+          "picker_tasks": int(stats.get("p3_tasks", 0)), "picker_pairs": int(stats.get("p3_pairs", 0)),
+          "markers_with_pairs": int((res["n_sel"] > 0).sum()), "pairs_ranked": int(len(res["f"]))}
+    return c5, dt * 1e3
 
 
 def run_b200(args, rank, world, local_rank):
@@ -244,11 +282,17 @@ def run_b200(args, rank, world, local_rank):
     het_dev = d_het.cpu().numpy().view(po.THAL_OUT_DTYPE)
     assert het_dev.tobytes() == out_np["het"].tobytes(), "device-resident and host-buffer paths disagree"
 
+    # ---- secondary: BASELINE config 5, KASP design of synthetic markers (markers/s) ------------
+    c5 = None
+    c5_ms = 0.0
+    if args.markers > 0:
+        c5, c5_ms = run_config5(args, rank, local_rank, barrier)
+
     # ---- reduce over ranks: max time ------------------------------------------------
-    times = torch.tensor([dev_ms, e2e_s * 1e3, het_ms, hp_ms, tm_ms], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_s * 1e3, het_ms, hp_ms, tm_ms, c5_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, het_ms, hp_ms, tm_ms = [float(x) for x in times.cpu()]
+    dev_ms, e2e_ms, het_ms, hp_ms, tm_ms, c5_ms = [float(x) for x in times.cpu()]
 
     if rank == 0:
         evals = EVALS_PER_PAIR * n * world * args.steps
@@ -281,6 +325,11 @@ def run_b200(args, rank, world, local_rank):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "kernel_ms": {"heterodimer": het_ms, "hairpin_x2": hp_ms, "tm_x2": tm_ms},
                 "heterodimers_per_s": n * world / (het_ms * 1e-3), "hairpins_per_s": 2 * n * world / (hp_ms * 1e-3)}
+        if c5 is not None:
+            c5["markers_per_s"] = args.markers * world / (c5_ms * 1e-3)
+            c5["ms"] = c5_ms
+            c5["thal_evaluations_per_s"] = c5["thal_evaluations_rank0"] * world / (c5_ms * 1e-3)
+            line["config5_kasp_design"] = c5
         if world == 1 and not args.no_cpu_baseline:
             from oracle.oracle import Oracle, build
             build()

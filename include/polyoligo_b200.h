@@ -318,6 +318,9 @@ int po_p3_design_fixed_batch(po_ctx *ctx, const po_p3_settings *s, const char *t
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context has launched since po_init. */
 int64_t po_launch_count(const po_ctx *ctx);
+/* Number of thal evaluations (hairpin / dimer items of any entry point, including the ones the
+ * primer picker and the ranking issue internally) this context has run since po_init. */
+int64_t po_thal_item_count(const po_ctx *ctx);
 /* DP relaxations (SURVEY 8d work unit, counted exactly as the upstream
  * algorithm performs them) of one po_thal_batch over host buffers; runs the
  * instrumented kernel variant, not for timing. */

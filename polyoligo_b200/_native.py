@@ -110,6 +110,7 @@ EXPORTS = {
                                            C.c_void_p]),
     "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "po_launch_count": (C.c_int64, [C.c_void_p]),
+    "po_thal_item_count": (C.c_int64, [C.c_void_p]),
     "po_thal_count_relaxations": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
                                             C.POINTER(C.c_int64)]),
     "po_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -321,6 +322,9 @@ class Context:
 
     def launch_count(self):
         return load().po_launch_count(self._h)
+
+    def thal_item_count(self):
+        return load().po_thal_item_count(self._h)
 
     def measure_fp64_peak(self):
         v = C.c_double()

@@ -199,6 +199,7 @@ struct po_ctx {
     int num_sms = 0;
     std::string err;
     int64_t launches = 0;
+    int64_t thal_items = 0;  // thal evaluations requested since po_init
     // grow-only device scratch
     DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow;
     DevBuf scratch[12];
@@ -318,6 +319,8 @@ extern "C" int po_set_conditions(po_ctx* ctx, double mv, double dv, double dntp,
     return PO_OK;
 }
 
+extern "C" int64_t po_thal_item_count(const po_ctx* ctx) { return ctx ? ctx->thal_items : 0; }
+
 extern "C" int64_t po_launch_count(const po_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // ============================================================================
@@ -410,6 +413,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
 template <bool COUNT>
 static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out, cudaStream_t st) {
     if (n == 0) return PO_OK;
+    ctx->thal_items += n;
     int rc = ensure(ctx, ctx->overflow, 2 * sizeof(long long) * (size_t)n);
     if (rc) return rc;
     unsigned long long* ctr = ctx->d_ctr;

@@ -213,3 +213,54 @@ def test_design_primers_dict_matches_oracle(ctx, oracle):
     assert [res["PRIMER_RIGHT_%d_SEQUENCE" % i] for i in range(len(ref2))] == [e["right"]["seq"] for e in ref2]
     assert p3b.designPrimers({"SEQUENCE_TEMPLATE": t, "SEQUENCE_PRIMER": "ACGTACGTACGTACGTACGTAA"}).get("PRIMER_ERROR")
     p3b.resetP3Globals()
+
+
+def _rows_for_task(fixed, pairs, n_pairs, tasks, t):
+    n = int(n_pairs[t])
+    others = pairs[t, :n]["other"]
+    oseq = _native.unpack(others["seq"]) if n else []
+    fseq = _native.unpack(fixed[t:t + 1]["seq"])[0]
+    rows = []
+    for i in range(n):
+        p = pairs[t, i]
+        tail = (p["pair_penalty"], p["compl_any_th"], p["compl_end_th"], p["product_size"], p["size_range"])
+        if tasks[t]["side"] == 1:
+            rows.append((fixed[t], fseq, others[i], oseq[i]) + tail)
+        else:
+            rows.append((others[i], oseq[i], fixed[t], fseq) + tail)
+    return rows
+
+
+@pytest.mark.gpu
+def test_fixed_primer_design_depth_100_and_ties(ctx, oracle):
+    # the reference's default search depth (cli_kasp.py --depth 100): several proposal rounds per task
+    rng = np.random.default_rng(41)
+    s = _gpu_settings(100)
+    so = oracle_settings(KASP_GLOBALS, 100)
+    full = {**p3_oracle.DEFAULTS, **so}
+    t1 = rand_template(rng, 500, gc=0.47)
+    # a repeated block: candidates with identical sequence, Tm and penalty at two positions, so
+    # pair penalties tie and the order falls to the position rules; a small depth cuts inside ties
+    block = rand_template(rng, 45, gc=0.5)
+    t2 = rand_template(rng, 130, gc=0.5) + block + rand_template(rng, 25) + block + rand_template(rng, 40)
+    cases = []
+    for k, (t, depth) in enumerate(((t1, 100), (t2, 100), (t2, 3), (t2, 7))):
+        lefts = [r for r in p3_oracle.candidates(full, t, [0] * len(t), "L") if 40 <= r["start"] <= 110][:2]
+        rights = [r for r in p3_oracle.candidates(full, t, [0] * len(t), "R") if len(t) - 60 <= r["start"]][:1]
+        cases.append((t, depth, lefts, rights))
+    n_checked = 0
+    for t, depth, lefts, rights in cases:
+        s.num_return = depth
+        so["num_return"] = depth
+        tasks = np.array([(0, 1, r["start"], r["len"]) for r in lefts] + [(0, 2, r["start"], r["len"]) for r in rights],
+                         dtype=_native.P3_TASK_DTYPE)
+        fixed, pairs, n_pairs = ctx.p3_design_fixed(s, [t], tasks)
+        for i, r in enumerate(lefts + rights):
+            kw = {"left": r["seq"]} if i < len(lefts) else {"right": r["seq"]}
+            if t.upper().find(r["seq"] if i < len(lefts) else p3b._revcomp(r["seq"])) != \
+                    (r["start"] if i < len(lefts) else r["start"] - r["len"] + 1):
+                continue       # the given primer itself sits in the repeated block: the oracle finds the first copy
+            ref = p3_oracle.design(oracle, so, t, **kw)
+            _check_pairs(_rows_for_task(fixed, pairs, n_pairs, tasks, i), ref, "depth %d task %d" % (depth, i))
+            n_checked += len(ref)
+    assert n_checked > 150
