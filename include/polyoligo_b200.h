@@ -279,7 +279,8 @@ typedef struct {
     int32_t set;                  /* template the oligo was cut from                                 */
     int32_t flags;                /* PO_P3_*                                                          */
 } po_p3_oligo;                    /* 80 bytes                                                         */
-enum { PO_P3_OK = 1, PO_P3_SELF_DONE = 2, PO_P3_SELF_FAILED = 4, PO_P3_QUEUED = 8 };
+enum { PO_P3_OK = 1, PO_P3_SELF_DONE = 2, PO_P3_SELF_FAILED = 4, PO_P3_QUEUED = 8,
+       PO_P3_PRIMER_VALID = 16 /* passes Primer.is_valid (only with `valid` below) */ };
 
 typedef struct {
     int32_t set;                  /* template index                                                   */
@@ -309,11 +310,15 @@ int po_p3_candidates_batch(po_ctx *ctx, const po_p3_settings *s, const char *tmp
  * num_return complementary primers per task in libprimer3's order.  set_target is NULL or
  * 2 x n_sets (start, len; len <= 0: none).  fixed_out (n_tasks) receives the given primer's own
  * record (flags without PO_P3_OK: it violates the constraints and the task returns nothing);
- * pairs_out is n_tasks x num_return, n_pairs_out the valid count per task. */
+ * pairs_out is n_tasks x num_return, n_pairs_out the valid count per task.
+ * valid != NULL additionally runs Primer.is_valid (reference lib_primer3.py:66-97, what the KASP
+ * merge asks of every picked common primer, _lib_kasp.py:621-625) on each distinct picked
+ * primer under the context's own conditions and reports it as PO_P3_PRIMER_VALID in
+ * pairs_out[].other.flags. */
 int po_p3_design_fixed_batch(po_ctx *ctx, const po_p3_settings *s, const char *tmpl, const uint8_t *mask,
                              const int64_t *set_off, const int32_t *set_target, int64_t n_sets,
-                             const po_p3_task *tasks, int64_t n_tasks, po_p3_oligo *fixed_out,
-                             po_p3_pair *pairs_out, int32_t *n_pairs_out);
+                             const po_p3_task *tasks, int64_t n_tasks, const po_valid_params *valid,
+                             po_p3_oligo *fixed_out, po_p3_pair *pairs_out, int32_t *n_pairs_out);
 
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context has launched since po_init. */

@@ -75,7 +75,7 @@ P3_TASK_DTYPE = np.dtype([("set", "<i4"), ("side", "<i4"), ("start", "<i4"), ("l
 P3_PAIR_DTYPE = np.dtype([("other", P3_OLIGO_DTYPE), ("pair_penalty", "<f8"), ("compl_any_th", "<f8"),
                           ("compl_end_th", "<f8"), ("product_size", "<i4"), ("size_range", "<i4")])
 assert P3_OLIGO_DTYPE.itemsize == 80 and P3_PAIR_DTYPE.itemsize == 112 and P3_TASK_DTYPE.itemsize == 16
-P3_OK, P3_SELF_DONE, P3_SELF_FAILED = 1, 2, 4
+P3_OK, P3_SELF_DONE, P3_SELF_FAILED, P3_PRIMER_VALID = 1, 2, 4, 16
 
 
 # every symbol include/polyoligo_b200.h declares
@@ -106,8 +106,8 @@ EXPORTS = {
     "po_p3_candidates_batch": (C.c_int, [C.c_void_p, C.POINTER(P3Settings), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]),
     "po_p3_design_fixed_batch": (C.c_int, [C.c_void_p, C.POINTER(P3Settings), C.c_void_p, C.c_void_p, C.c_void_p,
-                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
-                                           C.c_void_p]),
+                                           C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(ValidParams),
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "po_launch_count": (C.c_int64, [C.c_void_p]),
     "po_thal_item_count": (C.c_int64, [C.c_void_p]),
@@ -293,20 +293,22 @@ class Context:
             self._check(load().po_p3_candidates_batch(*args, out.ctypes.data, out.size), "po_p3_candidates_batch")
         return list_off, out
 
-    def p3_design_fixed(self, settings, templates, tasks, masks=None, targets=None):
-        """designPrimers with one primer given: (fixed records, pairs[n_tasks, num_return], n_pairs)."""
+    def p3_design_fixed(self, settings, templates, tasks, masks=None, targets=None, valid=None):
+        """designPrimers with one primer given: (fixed records, pairs[n_tasks, num_return], n_pairs).
+        ``valid`` (ValidParams) also evaluates Primer.is_valid of the picked primers (P3_PRIMER_VALID)."""
         blob, off, m = self._p3_inputs(templates, masks)
         n = len(off) - 1
         tasks = np.ascontiguousarray(tasks, dtype=P3_TASK_DTYPE)
         nt = len(tasks)
         tg = None if targets is None else np.ascontiguousarray(targets, dtype=np.int32).reshape(n, 2)
         fixed = np.zeros(nt, dtype=P3_OLIGO_DTYPE)
-        pairs = np.zeros((nt, settings.num_return), dtype=P3_PAIR_DTYPE)
+        pairs = np.empty((nt, settings.num_return), dtype=P3_PAIR_DTYPE)   # rows beyond n_pairs stay unset
         n_pairs = np.zeros(nt, dtype=np.int32)
         self._check(load().po_p3_design_fixed_batch(
             self._h, C.byref(settings), blob.ctypes.data if blob.size else None,
             m.ctypes.data if m is not None and m.size else None, off.ctypes.data,
-            tg.ctypes.data if tg is not None else None, n, tasks.ctypes.data, nt, fixed.ctypes.data,
+            tg.ctypes.data if tg is not None else None, n, tasks.ctypes.data, nt,
+            C.byref(valid) if valid is not None else None, fixed.ctypes.data,
             pairs.ctypes.data, n_pairs.ctypes.data), "po_p3_design_fixed_batch")
         return fixed, pairs, n_pairs
 

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po_thal_out* __restrict__ out,
        const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
        const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
-       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax, int end_mode) {
+       long long* overflow, unsigned long long* overflow_n, unsigned long long* relax, int end_mode,
+       po_thal_out* __restrict__ out2) {
     using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem);
@@ -91,7 +92,8 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                 if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
                 continue;
             }
-            thal_dimer_warp<PO_DIMER_GROUP, CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item, relax);
+            thal_dimer_warp<PO_DIMER_GROUP, CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item,
+                                                        out2 ? out2 + item : nullptr, relax);
         }
     }
 }
@@ -380,7 +382,7 @@ template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
 static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4* B, long long n, po_thal_out* out,
                        unsigned long long* work, const long long* list, const unsigned long long* list_n,
                        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax,
-                       int end_mode = 0) {
+                       int end_mode = 0, po_thal_out* out2 = nullptr) {
     using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
     const size_t smem = sizeof(SmemTables) + sizeof(SmemExtra) + WARPS * sizeof(Ws);
     auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN>;
@@ -398,7 +400,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
     }
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, B, n, out, ctx->d_tables, ctx->K, work, list, list_n, overflow,
-                                                     overflow_n, relax, end_mode);
+                                                     overflow_n, relax, end_mode, out2);
     ctx->launches++;
     CK(cudaGetLastError());
     return PO_OK;
@@ -410,10 +412,13 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
 // queued for the next one (reporter-tailed KASP pairs, then low-complexity /
 // 60-mer inputs whose DP table is dense).  Counters: ctr[0] work1, ctr[1]
 // list1_n, ctr[2] work2, ctr[3] list2_n, ctr[4] work3, ctr[5] unused, ctr[7] relaxations.
+// d_out2 (dimer types only): ANY result to d_out and END1 result to d_out2 from ONE table fill
+// (libprimer3 asks for both on every oligo and pair; the fill is > 90 % of the work).
 template <bool COUNT>
-static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out, cudaStream_t st) {
+static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out, cudaStream_t st,
+                    void* d_out2 = nullptr) {
     if (n == 0) return PO_OK;
-    ctx->thal_items += n;
+    ctx->thal_items += d_out2 ? 2 * n : n;
     int rc = ensure(ctx, ctx->overflow, 2 * sizeof(long long) * (size_t)n);
     if (rc) return rc;
     unsigned long long* ctr = ctx->d_ctr;
@@ -436,12 +441,17 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
         return PO_E_INVALID;
     }
     const int em = type == PO_THAL_END1 ? 1 : type == PO_THAL_END2 ? 2 : 0;
-    if (cap == 192) rc = launch_thal<192, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em);
-    else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em);
-    else rc = launch_thal<256, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em);
+    po_thal_out* out2 = (po_thal_out*)d_out2;
+    if (out2 && type != PO_THAL_ANY) {
+        ctx->err = "po_thal: the fused ANY + END1 form needs type ANY";
+        return PO_E_INVALID;
+    }
+    if (cap == 192) rc = launch_thal<192, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
+    else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
+    else rc = launch_thal<256, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
     if (rc) return rc;
-    if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em))) return rc;
-    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em);
+    if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em, out2))) return rc;
+    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em, out2);
 }
 
 extern "C" int po_thal_batch_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out,

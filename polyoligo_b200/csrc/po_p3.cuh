@@ -321,7 +321,7 @@ __global__ void k_p3_propose(const po_p3_task* __restrict__ tasks, long long n_t
         tar_l = set_target[2 * tk.set + 1];
     }
     const int need = S.num_return - st.n_found;
-    const int want = st.tie_mode ? P3_K : min(P3_K, need + need / 4 + 4);
+    const int want = st.tie_mode ? P3_K : min(P3_K, need + need / 16 + 2);  // few alignments fail the 47 C limits
     int r = 0, cur = st.cursor, stop_after = 0;
     while (cur < n && r < want && !stop_after) {
         const int c = cur + lane;
@@ -494,12 +494,12 @@ __global__ void k_p3_accept(const po_p3_task* __restrict__ tasks, long long n_ta
     if (!st.done) atomicAdd(&ctr[2], 1ull);
 }
 
-// One thread per task: order the accepted pairs and emit the best num_return
-__global__ void k_p3_finalize(const po_p3_task* __restrict__ tasks, long long n_tasks, const po_p3_settings S,
-                              const long long* __restrict__ list_off, const po_p3_oligo* __restrict__ pool,
-                              const po_p3_oligo* __restrict__ fixed, const P3TaskState* __restrict__ state,
-                              P3Result* __restrict__ results, int rcap, po_p3_pair* __restrict__ out,
-                              int32_t* __restrict__ n_out) {
+// One thread per task: order the accepted pairs (full libprimer3 pair order); the chosen
+// candidates are queued once for the optional Primer.is_valid pass.
+__global__ void k_p3_order(const po_p3_task* __restrict__ tasks, long long n_tasks, const po_p3_settings S,
+                           const long long* __restrict__ list_off, po_p3_oligo* __restrict__ pool,
+                           const P3TaskState* __restrict__ state, P3Result* __restrict__ results, int rcap,
+                           int want_valid, unsigned long long* __restrict__ ctr, long long* __restrict__ used_list) {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= n_tasks) return;
     const po_p3_task tk = tasks[t];
@@ -528,7 +528,37 @@ __global__ void k_p3_finalize(const po_p3_task* __restrict__ tasks, long long n_
         }
         R[j + 1] = x;
     }
-    const int m = min(n, S.num_return);
+    if (want_valid) {
+        const int m = min(n, S.num_return);
+        for (int i = 0; i < m; ++i) {
+            const long long c = off + R[i].cand;
+            const int old = atomicOr(&pool[c].flags, PO_P3_QUEUED);
+            if (!(old & PO_P3_QUEUED)) used_list[atomicAdd(&ctr[3], 1ull)] = c;
+        }
+    }
+}
+
+// Primer.is_valid of the queued candidates (props computed under the caller's conditions)
+__global__ void k_p3_scatter_valid(const long long* __restrict__ used_list, long long n,
+                                   const po_oligo_props* __restrict__ props, po_p3_oligo* __restrict__ pool) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    po_p3_oligo& r = pool[used_list[i]];
+    int fl = r.flags & ~PO_P3_QUEUED;
+    if (props[i].flags & PO_PRIMER_VALID) fl |= PO_P3_PRIMER_VALID;
+    r.flags = fl;
+}
+
+__global__ void k_p3_emit(const po_p3_task* __restrict__ tasks, long long n_tasks, const po_p3_settings S,
+                          const long long* __restrict__ list_off, const po_p3_oligo* __restrict__ pool,
+                          const P3TaskState* __restrict__ state, const P3Result* __restrict__ results, int rcap,
+                          po_p3_pair* __restrict__ out, int32_t* __restrict__ n_out) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= n_tasks) return;
+    const po_p3_task tk = tasks[t];
+    const long long off = list_off[2ll * tk.set + (tk.side == 1 ? 1 : 0)];
+    const P3Result* R = results + t * rcap;
+    const int m = min(state[t].n_found, S.num_return);
     for (int i = 0; i < m; ++i) {
         po_p3_pair p;
         p.other = pool[off + R[i].cand];
@@ -656,8 +686,8 @@ extern "C" int po_p3_candidates_batch(po_ctx* ctx, const po_p3_settings* s, cons
 
 extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, const char* tmpl, const uint8_t* mask,
                                         const int64_t* set_off, const int32_t* set_target, int64_t n_sets,
-                                        const po_p3_task* tasks, int64_t n_tasks, po_p3_oligo* fixed_out,
-                                        po_p3_pair* pairs_out, int32_t* n_pairs_out) {
+                                        const po_p3_task* tasks, int64_t n_tasks, const po_valid_params* valid,
+                                        po_p3_oligo* fixed_out, po_p3_pair* pairs_out, int32_t* n_pairs_out) {
     if (!ctx || !set_off || n_sets < 0 || n_tasks < 0 || (n_tasks > 0 && (!tasks || !pairs_out || !n_pairs_out)))
         return PO_E_INVALID;
     int rc = p3_check_settings(ctx, s);
@@ -752,8 +782,7 @@ extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, co
         k_p3_gather_fixed<<<tb, threads, 0, st>>>(d_fixed, n_tasks, sa);
         ctx->launches++;
         P3CK(cudaGetLastError());
-        if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, sa, nullptr, n_tasks, t0, st))) return restore(rc);
-        if ((rc = thal_dev<false>(ctx, PO_THAL_END1, sa, nullptr, n_tasks, t1, st))) return restore(rc);
+        if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, sa, nullptr, n_tasks, t0, st, t1))) return restore(rc);
         if ((rc = thal_dev<false>(ctx, PO_THAL_HAIRPIN, sa, nullptr, n_tasks, t2, st))) return restore(rc);
         k_p3_fixed_self<<<tb, threads, 0, st>>>(n_tasks, t0, t1, t2, *s, d_fixed, d_state);
         ctx->launches++;
@@ -774,8 +803,7 @@ extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, co
             const unsigned gb = (unsigned)((n_self + threads - 1) / threads);
             k_p3_gather_self<<<gb, threads, 0, st>>>((const long long*)sb[15].p, n_self, d_pool, sa);
             ctx->launches++;
-            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, sa, nullptr, n_self, t0, st))) return restore(rc);
-            if ((rc = thal_dev<false>(ctx, PO_THAL_END1, sa, nullptr, n_self, t1, st))) return restore(rc);
+            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, sa, nullptr, n_self, t0, st, t1))) return restore(rc);
             if ((rc = thal_dev<false>(ctx, PO_THAL_HAIRPIN, sa, nullptr, n_self, t2, st))) return restore(rc);
             k_p3_scatter_self<<<gb, threads, 0, st>>>((const long long*)sb[15].p, n_self, t0, t1, t2, *s, d_pool);
             ctx->launches++;
@@ -786,8 +814,7 @@ extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, co
             k_p3_gather_pairs<<<gb, threads, 0, st>>>((const long long*)sb[14].p, n_pair, d_tasks, d_list_off, d_pool,
                                                       d_fixed, (const int32_t*)sb[12].p, sa, sbq);
             ctx->launches++;
-            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, sa, sbq, n_pair, t0, st))) return restore(rc);
-            if ((rc = thal_dev<false>(ctx, PO_THAL_END1, sa, sbq, n_pair, t1, st))) return restore(rc);
+            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, sa, sbq, n_pair, t0, st, t1))) return restore(rc);
             if ((rc = thal_dev<false>(ctx, PO_THAL_END2, sa, sbq, n_pair, t2, st))) return restore(rc);
             k_p3_scatter_pairs<<<gb, threads, 0, st>>>((const long long*)sb[14].p, n_pair, t0, t1, t2,
                                                        (double*)sb[13].p);
@@ -804,8 +831,34 @@ extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, co
         if (h_ctr[2] == 0) break;
     }
     ctx->K = saved;
-    k_p3_finalize<<<tb, threads, 0, st>>>(d_tasks, n_tasks, *s, d_list_off, d_pool, d_fixed, d_state,
-                                          (P3Result*)sb[16].p, rcap, (po_p3_pair*)sb[24].p, (int32_t*)sb[25].p);
+    P3CK(cudaMemsetAsync(d_ctr, 0, 8 * 4, st));
+    k_p3_order<<<tb, threads, 0, st>>>(d_tasks, n_tasks, *s, d_list_off, d_pool, d_state, (P3Result*)sb[16].p, rcap,
+                                       valid ? 1 : 0, d_ctr, (long long*)sb[15].p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (valid) {
+        // Primer.is_valid (reference lib_primer3.py:66-97) of every picked primer, under the
+        // context's own conditions (ThermoAnalysis()), once per distinct candidate
+        CK(cudaMemcpyAsync(h_ctr, d_ctr, 8 * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const long long n_used = (long long)h_ctr[3];
+        if (n_used > 0) {
+            const unsigned gb = (unsigned)((n_used + threads - 1) / threads);
+            if ((rc = ensure(ctx, ctx->props, sizeof(po_oligo_props) * (size_t)n_used))) return rc;
+            k_p3_gather_self<<<gb, threads, 0, st>>>((const long long*)sb[15].p, n_used, d_pool, sa);
+            ctx->launches++;
+            if ((rc = thal_dev<false>(ctx, PO_THAL_HAIRPIN, sa, nullptr, n_used, t0, st))) return rc;
+            if ((rc = thal_dev<false>(ctx, PO_THAL_ANY, sa, nullptr, n_used, t1, st))) return rc;
+            k_props<<<gb, threads, 0, st>>>(sa, n_used, t0, t1, ctx->K, *valid, 1, (po_oligo_props*)ctx->props.p);
+            ctx->launches++;
+            k_p3_scatter_valid<<<gb, threads, 0, st>>>((const long long*)sb[15].p, n_used,
+                                                       (const po_oligo_props*)ctx->props.p, d_pool);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    k_p3_emit<<<tb, threads, 0, st>>>(d_tasks, n_tasks, *s, d_list_off, d_pool, d_state, (const P3Result*)sb[16].p,
+                                      rcap, (po_p3_pair*)sb[24].p, (int32_t*)sb[25].p);
     ctx->launches++;
     CK(cudaGetLastError());
     if (fixed_out) CK(cudaMemcpyAsync(fixed_out, d_fixed, sizeof(po_p3_oligo) * nt, cudaMemcpyDeviceToHost, st));

@@ -125,7 +125,7 @@ __device__ __forceinline__ void dimer_scan(const Grp<G>& g, const TabAddr& A, co
 template <int G, int CAP, bool COUNT>
 __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const TabAddr& A, DimerWs<CAP>& ws,
                                 const uint4 oa, const uint4 ob, const PoConsts& K, const bool end_only,
-                                po_thal_out* out, unsigned long long* relax) {
+                                po_thal_out* out, po_thal_out* out2, unsigned long long* relax) {
     const int lane = threadIdx.x & 31;
     const Grp<G> g = Grp<G>::make();
     const Grp<32> gw = Grp<32>::make();
@@ -138,7 +138,10 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
     r.align_end_1 = r.align_end_2 = -1;
     if (po_bad(oa) || po_bad(ob) || len1 == 0 || len2 == 0 || len1 > PO_MAX_OLIGO_LEN || len2 > PO_MAX_OLIGO_LEN) {
         r.flags = PO_ITEM_SKIPPED;
-        if (lane == 0) *out = r;
+        if (lane == 0) {
+            *out = r;
+            if (out2) *out2 = r;
+        }
         return;
     }
     __syncwarp();
@@ -309,11 +312,17 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         }
     }
 
+    // The filled table serves every alignment type: with out2 the ANY result goes to `out` and
+    // the END1 result (same fill, end scan over the last row only) to `out2`.
+    const int npass = out2 ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+    const bool eo = pass == 1 ? true : end_only;
+    po_thal_out* dst = pass == 1 ? out2 : out;
     // ---- end scan: minimum dG over all cells, first in row-major order wins ---
     // (thal types END1 / END2: only the cells of the last row, i == len1)
     double bestG = PO_INF;
     int bestK = KEY_NONE;
-    for (int k0 = end_only ? ws.start[len1] : 0; k0 < ncell; k0 += 32) {
+    for (int k0 = eo ? ws.start[len1] : 0; k0 < ncell; k0 += 32) {
         const bool act = k0 + lane < ncell;
         const int k = act ? k0 + lane : 0;
         const uint32_t code = ws.code[k];
@@ -327,11 +336,11 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             bestK = k;
         }
     }
-    if (COUNT) cnt += (lane == 0) ? (end_only ? len2 : len1 * len2) : 0;
+    if (COUNT) cnt += (lane == 0) ? (eo ? len2 : len1 * len2) : 0;
     double wG = PO_INF;
     int wK = KEY_NONE;
     const int gsrc = gw.argmin(bestG, bestK, &wG, &wK);
-    if (COUNT && relax) {
+    if (COUNT && relax && pass == npass - 1) {
         __syncwarp();
         const unsigned total_cnt = __reduce_add_sync(FULL, (unsigned)cnt);
         if (lane == 0) atomicAdd(relax, (unsigned long long)total_cnt);
@@ -339,8 +348,8 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
     if (gsrc < 0 || !fin(wG)) {
         // upstream falls back to cell (1,1); without a finite value there: no structure, tm = 0
         if (!(ROWMASK(1) & 1ull)) {
-            if (lane == 0) *out = r;
-            return;
+            if (lane == 0) *dst = r;
+            continue;
         }
         wK = 0;
     }
@@ -398,21 +407,22 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         j = j - (sum - l1) - 1;
         ++npairs;
     }
-#undef ROWMASK
-#undef LSH_AT
-#undef RSH_AT
-
     // ---- drawDimer ---------------------------------------------------------------
     const int N = npairs - 1;  // (2 * npairs) / 2 - 1
     const double t = (dH / (dS + (N * K.salt_corr) + RC)) - PO_ABSOLUTE_ZERO;
     const double dG = dH - (K.temp_k * (dS + (N * K.salt_corr)));
     const double S = dS + (N * K.salt_corr);
-    r.tm = t;
-    r.dg = dG;
-    r.dh = dH;
-    r.ds = S;
-    r.flags = PO_ITEM_STRUCTURE_FOUND | (sym ? PO_ITEM_SYMMETRIC : 0);
-    r.align_end_1 = (int16_t)bestI;
-    r.align_end_2 = (int16_t)bestJ;
-    if (lane == 0) *out = r;
+    po_thal_out res = r;
+    res.tm = t;
+    res.dg = dG;
+    res.dh = dH;
+    res.ds = S;
+    res.flags = PO_ITEM_STRUCTURE_FOUND | (sym ? PO_ITEM_SYMMETRIC : 0);
+    res.align_end_1 = (int16_t)bestI;
+    res.align_end_2 = (int16_t)bestJ;
+    if (lane == 0) *dst = res;
+    }
+#undef ROWMASK
+#undef LSH_AT
+#undef RSH_AT
 }

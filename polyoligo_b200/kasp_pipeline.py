@@ -180,14 +180,26 @@ def _design_chunk(ctx, data, c0, c1, templates, length, lo, hi, settings, depth,
     off = np.arange(m + 1, dtype=np.int64) * length
     # ---- a5 + a6, one pass per search type --------------------------------------------------------
     count = np.zeros(m, dtype=np.int64)
-    acc = {k: [] for k in ("marker", "slot", "other", "order")}
+    acc = {k: [] for k in ("marker", "slot", "other")}
     seen_keys = np.zeros(0, dtype=np.int64)
     done_masks = []
+    # A primer that can pair with a marker primer lies inside the largest product that starts / ends
+    # at that marker primer; mask differences outside that window cannot change the picker's answer.
+    maxprod = int(max(settings.size_hi[:settings.n_size_ranges]))
+    slot_is_r = (np.arange(slots) % 2 == 1)[None, :]
+    big = 1 << 30
+    lo_pos = np.where(keep & slot_is_r, p_start - maxprod + 1, big).min(axis=1)      # left candidates of R tasks
+    hi_pos = np.where(keep & ~slot_is_r, p_start + maxprod - 1, -big).max(axis=1)    # right candidates of F tasks
+    # the marker primers themselves must stay clear of excluded bases as well
+    own_lo = np.where(keep, np.where(slot_is_r, p_start - p_len + 1, p_start), big).min(axis=1)
+    own_hi = np.where(keep, np.where(slot_is_r, p_start, p_start + p_len - 1), -big).max(axis=1)
+    pos = np.arange(length)[None, :]
+    window = (pos >= np.minimum(lo_pos, own_lo)[:, None]) & (pos <= np.maximum(hi_pos, own_hi)[:, None])
     for step, name in enumerate(types_):
         mask = masks[name]
         active = count < depth
         for prev in done_masks:                           # same mask, same answer: nothing new to merge
-            active &= (mask != prev).any(axis=1)
+            active &= ((mask != prev) & window).any(axis=1)
         done_masks.append(mask)
         tsel = active[mk]
         if not tsel.any():
@@ -198,40 +210,38 @@ def _design_chunk(ctx, data, c0, c1, templates, length, lo, hi, settings, depth,
         tasks["side"] = 1 + (ts_ % 2)
         tasks["start"] = p_start[tm_, ts_]
         tasks["len"] = p_len[tm_, ts_]
-        _, pairs, n_pairs = ctx.p3_design_fixed(settings, (blob, off), tasks, mask)
+        # picker + Primer.is_valid of every picked common primer, in one device call
+        _, pairs, n_pairs = ctx.p3_design_fixed(settings, (blob, off), tasks, mask, valid=vparams)
         if stats is not None:
             stats["p3_tasks"] = stats.get("p3_tasks", 0) + len(tasks)
             stats["p3_pairs"] = stats.get("p3_pairs", 0) + int(n_pairs.sum())
-        t_idx, r_idx = np.nonzero(np.arange(depth)[None, :] < n_pairs[:, None])
+        oth = pairs["other"]
+        cand2d = (np.arange(depth)[None, :] < n_pairs[:, None]) & ((oth["flags"] & _native.P3_PRIMER_VALID) != 0)
+        t_idx, r_idx = np.nonzero(cand2d)
         if len(t_idx) == 0:
             continue
-        other = pairs["other"][t_idx, r_idx]
         e_marker, e_slot = tm_[t_idx], ts_[t_idx]
-        # Primer.is_valid of the picked common primers, once per distinct oligo of a marker
-        okey = (e_marker * 2 + (e_slot % 2)) * 1024 * 64 + other["start"].astype(np.int64) * 64 + other["len"]
-        uniq, first, inv = np.unique(okey, return_index=True, return_inverse=True)
-        props = ctx.oligo_props_batch(np.ascontiguousarray(other["seq"][first]), vparams)
-        valid = ((props["flags"] & _native.PRIMER_VALID) != 0)[inv]
-        # not already in the repository (same marker primer slot and same common primer)
-        pkey = (e_marker * 32 + e_slot) * 1024 * 64 + other["start"].astype(np.int64) * 64 + other["len"]
-        is_new = ~np.isin(pkey, seen_keys)
-        cand = valid & is_new
+        if len(seen_keys) or step + 1 < len(types_):
+            # same marker primer slot and same common primer: already in the repository?
+            pkey = (e_marker * 32 + e_slot) * 1024 * 64 + oth["start"][t_idx, r_idx].astype(np.int64) * 64 + \
+                oth["len"][t_idx, r_idx]
+            if len(seen_keys):
+                fresh = ~np.isin(pkey, seen_keys)
+                t_idx, r_idx, e_marker, e_slot, pkey = (x[fresh] for x in (t_idx, r_idx, e_marker, e_slot, pkey))
+        else:
+            pkey = None
         # round-robin pop order: rank r first, then marker-primer order; cut at `depth` per marker
-        order_key = (e_marker * depth + r_idx) * 32 + e_slot
-        ci = np.flatnonzero(cand)
-        ci = ci[np.argsort(order_key[ci], kind="stable")]
-        cm = e_marker[ci]
-        first_of_marker = np.searchsorted(cm, cm, side="left")
-        rank = np.arange(len(ci)) - first_of_marker
-        take = rank < (depth - count[cm])
-        ci = ci[take]
-        # the reference tests is_new for every popped pair, so rejected pairs are never added later
-        # either: identical inputs give identical answers in every later pass
+        order = np.argsort((e_marker * depth + r_idx) * 32 + e_slot, kind="stable")
+        cm = e_marker[order]
+        rank = np.arange(len(order)) - np.searchsorted(cm, cm, side="left")
+        ci = order[rank < (depth - count[cm])]
+        # (pairs the reference pops but rejects are never added later either: identical inputs
+        # give identical answers in every later pass)
         acc["marker"].append(e_marker[ci])
         acc["slot"].append(e_slot[ci])
-        acc["other"].append(other[ci])
-        acc["order"].append(np.full(len(ci), step, dtype=np.int64))
-        seen_keys = np.concatenate([seen_keys, pkey[ci]])
+        acc["other"].append(oth[t_idx[ci], r_idx[ci]])
+        if pkey is not None:
+            seen_keys = np.concatenate([seen_keys, pkey[ci]])
         count += np.bincount(e_marker[ci], minlength=m)
     if acc["marker"]:
         e_marker = np.concatenate(acc["marker"])
