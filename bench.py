@@ -158,7 +158,7 @@ def run_config5(args, rank, local_rank, barrier):
     lp.set_tm_delta(5.0)
     dyes = ("GAAGGTCGGAGTCAACGGATT", "GAAGGTGACCAAGTTCATGCT")
     kctx = get_context(local_rank)
-    kp.design_markers_arrays(kp.synth_config5(128, seed=1), n_primers=10, reporters=dyes, device=local_rank)
+    kp.design_markers_arrays(kp.synth_config5(args.markers, seed=1), n_primers=10, reporters=dyes, device=local_rank)  # warm-up
     data = kp.synth_config5(args.markers, seed=kp.CONFIG5_SEED + rank)
     stats = {}
     items0, launches0 = kctx.thal_item_count(), kctx.launch_count()

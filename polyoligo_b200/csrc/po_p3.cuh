@@ -304,7 +304,7 @@ __global__ void k_p3_propose(const po_p3_task* __restrict__ tasks, long long n_t
                              po_p3_oligo* __restrict__ pool, const po_p3_oligo* __restrict__ fixed,
                              P3TaskState* __restrict__ state, int32_t* __restrict__ prop,
                              unsigned long long* __restrict__ ctr, long long* __restrict__ self_list,
-                             long long* __restrict__ pair_list) {
+                             long long* __restrict__ pair_list, int margin_div) {
     const long long t = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (t >= n_tasks) return;
@@ -321,7 +321,7 @@ __global__ void k_p3_propose(const po_p3_task* __restrict__ tasks, long long n_t
         tar_l = set_target[2 * tk.set + 1];
     }
     const int need = S.num_return - st.n_found;
-    const int want = st.tie_mode ? P3_K : min(P3_K, need + need / 16 + 2);  // few alignments fail the 47 C limits
+    const int want = st.tie_mode ? P3_K : min(P3_K, need + need / margin_div + 2);  // few alignments fail the limits
     int r = 0, cur = st.cursor, stop_after = 0;
     while (cur < n && r < want && !stop_after) {
         const int c = cur + lane;
@@ -789,11 +789,15 @@ extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, co
         P3CK(cudaGetLastError());
     }
     const unsigned wb = (unsigned)((n_tasks * 32 + threads - 1) / threads);
+    // over-proposal per round: need + need / margin_div + 2 candidates (tunable for experiments)
+    const char* md = getenv("PO_P3_MARGIN_DIV");
+    const int margin_div = md && atoi(md) > 0 ? atoi(md) : 16;
     unsigned long long h_ctr[4];
     for (int round = 0; round < 100000; ++round) {
         P3CK(cudaMemsetAsync(d_ctr, 0, 8 * 4, st));
         k_p3_propose<<<wb, threads, 0, st>>>(d_tasks, n_tasks, *s, d_target, d_list_off, d_pool, d_fixed, d_state,
-                                             (int32_t*)sb[12].p, d_ctr, (long long*)sb[15].p, (long long*)sb[14].p);
+                                             (int32_t*)sb[12].p, d_ctr, (long long*)sb[15].p, (long long*)sb[14].p,
+                                             margin_div);
         ctx->launches++;
         P3CK(cudaGetLastError());
         P3CK(cudaMemcpyAsync(h_ctr, d_ctr, 8 * 4, cudaMemcpyDeviceToHost, st));

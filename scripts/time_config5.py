@@ -21,7 +21,7 @@ for name in ("kasp_enumerate", "oligo_props_batch", "p3_design_fixed", "annotate
         return w
     setattr(ctx, name, wrap())
 dyes = ("GAAGGTCGGAGTCAACGGATT", "GAAGGTGACCAAGTTCATGCT")
-kp.design_markers_arrays(kp.synth_config5(128, seed=1), n_primers=10, reporters=dyes)
+kp.design_markers_arrays(kp.synth_config5(n, seed=1), n_primers=10, reporters=dyes, chunk=chunk)   # same-size warm-up
 T.clear()
 data = kp.synth_config5(n)
 t0 = time.perf_counter()
