@@ -11,7 +11,7 @@ from copy import deepcopy
 
 import numpy as np
 
-from . import _native, lib_primer3
+from . import _native, lib_primer3, lib_utils
 from .thermoanalysis import get_context
 
 _CODE = np.full(256, 255, dtype=np.uint8)
@@ -91,6 +91,10 @@ def check_heterodimerization_batch(pps, device=None):
 
 
 class PCR(lib_primer3.PCR):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.is_indel = None
+
     def check_heterodimerization(self):
         check_heterodimerization_batch(self.pps)
 
@@ -263,5 +267,83 @@ def design_markers(hrois, n_primers=10, reporters=None, device=None):
     for pcr in pcrs:
         pcr.add_reporter_dyes(reporters or ("", ""))
     lib_primer3.add_mutations_batch(pcrs, [list(h.mutations) for h in hrois], device)
+    for pcr, hroi in zip(pcrs, hrois):
+        if hroi.mutations and hasattr(hroi.mutations[0], "alt"):
+            for pp in pcr.pps:
+                lib_primer3.add_mutation_strings(pp, hroi.mutations)
     lib_primer3.rank_batch(pcrs, n_primers, "KASP", device, reporters=reporters)
     return pcrs
+
+
+# ---- report writer (reference _lib_kasp.py:14-45, 360-530) --------------------------------------
+DELIMITER = "\t"
+HEADER = ["marker", "chr", "pos", "ref", "alt", "start", "end", "direction", "type", "assay_id", "seq_5_3",
+          "seq_5_3_ambiguous", "primer_id", "goodness", "qcode", "length", "prod_size", "tm", "gc_content",
+          "will_dimerize", "n_offtargets", "max_aaf", "indels", "offtarget_products", "mutations"]
+
+
+def print_report_header(fp):
+    with open(fp, "w") as f:
+        f.write("{}\n".format(DELIMITER.join(HEADER)))
+
+
+def _allele_case(seq, n):
+    """lower case except the last n bases (the allele at the 3' end)"""
+    return seq.lower() if n == 0 else seq[:-n].lower() + seq[-n:]
+
+
+def print_report(pcr, fp):
+    """Per-marker TSV (<fp>.txt) and BED (<fp>.bed) of the pruned pairs, byte-identical to
+    reference _lib_kasp.py:367-530: REF / ALT / COM rows per assay, primer ids numbered by first
+    appearance of the (case-marked) sequence, round_tidy'd Tm / GC / aaf."""
+    order = ["REF", "ALT", "COM"]
+    seq_ids = {pt: [] for pt in order}
+    ppid = 0
+    with open(fp + ".txt", "w") as f, open(fp + ".bed", "w") as f_bed:
+        for score in sorted(set(pcr.pps_pruned.keys()), reverse=True):
+            for pp in pcr.pps_pruned[score]:
+                pp.id = ppid
+                dyes = {d: pp.primers[d].reporter for d in pp.primers}
+                marker_d, common_d = ("F", "R") if pp.dir == "F" else ("R", "F")
+                seqs = {"REF": _allele_case(pp.primers[marker_d].sequence, pcr.ref_n),
+                        "COM": pp.primers[common_d].sequence.lower(),
+                        "ALT": _allele_case(pp.primers["A"].sequence, pcr.alt_n)}
+                seqs_amb = {"REF": _allele_case(pp.primers[marker_d].sequence_ambiguous, pcr.ref_n),
+                            "COM": pp.primers[common_d].sequence_ambiguous.lower(),
+                            "ALT": _allele_case(pp.primers["A"].sequence_ambiguous, pcr.alt_n)}
+                ids = {}
+                for pt in order:
+                    if seqs[pt] not in seq_ids[pt]:
+                        seq_ids[pt].append(seqs[pt])
+                    ids[pt] = pt + "_" + str(seq_ids[pt].index(seqs[pt]))
+                offtargets = ",".join(pp.offtargets) or "NA"
+                for ptype, d in zip(order, [marker_d, "A", common_d]):
+                    mutations = ",".join(pp.primers[d].mutations) or "NA"
+                    will_dimerize, direction = (pp.alt_dimer, pp.dir) if d == "A" else (pp.ref_dimer, d)
+                    if pp.qcode == "":
+                        pp.qcode = "."
+                    ref, alt = pcr.ref, pcr.alt
+                    if pcr.is_indel == "ins":
+                        ref = "*"
+                    elif pcr.is_indel == "del":
+                        alt = "*"
+                    p = pp.primers[d]
+                    fields = [pcr.snp_id, pcr.chrom, int(pcr.pos), ref, alt, int(p.start), int(p.stop), direction,
+                              ptype, pp.id, dyes[d] + seqs[ptype], dyes[d] + seqs_amb[ptype],
+                              pcr.snp_id + "_" + ids[ptype], pp.goodness, pp.qcode, p.length, pp.product_size,
+                              lib_utils.round_tidy(p.tm, 3), lib_utils.round_tidy(p.gc_content, 3), will_dimerize,
+                              len(pp.offtargets), lib_utils.round_tidy(p.max_aaf, 2), pp.max_indel_size,
+                              offtargets, mutations]
+                    f.write("{}\n".format(DELIMITER.join(str(x) for x in fields)))
+                    bed = [pcr.chrom, int(p.start), int(p.stop),
+                           "{}_{}-{}".format(pcr.snp_id, ids[ptype], pp.goodness), "0",
+                           "+" if direction == "F" else "-"]
+                    f_bed.write("{}\n".format("\t".join(str(x) for x in bed)))
+                f.write("\n")
+                ppid += 1
+        if ppid == 0:
+            fields = [str(x) for x in (pcr.snp_id, pcr.chrom, int(pcr.pos), pcr.ref, pcr.alt)]
+            f.write(DELIMITER.join(fields + (len(HEADER) - 5) * ["NA"]) + "\n")
+            f.write("\n")
+        f.write("\n")
+

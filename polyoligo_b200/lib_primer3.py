@@ -55,6 +55,7 @@ class Primer:
         self.max_aaf = 0
         self.nN = 0
         self.sequence = None
+        self.sequence_ambiguous = None
         self.reporter = ""
         # attributes shared with the primer picker (reference lib_primer3.py:45-51)
         self.end_stability = None
@@ -151,6 +152,18 @@ class PrimerPair:
     def check_heterodimerization(self):
         check_heterodimerization_batch([self])
 
+    def add_mutations(self, mutations):
+        """reference lib_primer3.py:166-210, for one pair on the host (many pairs: add_mutations_batch
+        for the numbers, add_mutation_strings for the text)."""
+        add_mutation_strings(self, mutations)
+        for d, p in self.primers.items():
+            for m in mutations:
+                if p.start <= m.pos <= p.stop:
+                    p.max_aaf = max(p.max_aaf, m.aaf)
+        for m in mutations:
+            if self.primers["F"].start <= m.pos <= self.primers["R"].stop:
+                self.max_indel_size = max(self.max_indel_size, m.indel_size)
+
     def score(self, assay_name):
         self.goodness, self.qcode = scoring.get_score_fnc(assay_name)(self)
 
@@ -182,6 +195,12 @@ def _rank_inputs(pps, keys):
 class PCR:
     def __init__(self, chrom=None, primer_pairs=None, name=None, snp_id=None, pos=None, ref=None, alt=None):
         self.chrom, self.name, self.snp_id, self.pos, self.ref, self.alt = chrom, name, snp_id, pos, ref, alt
+        self.ref_n = len(ref) if ref is not None else 0       # reference lib_primer3.py:229-239
+        self.alt_n = len(alt) if alt is not None else 0
+        if self.ref == "":
+            self.ref = "*"
+        if self.alt == "":
+            self.alt = "*"
         self.pps = primer_pairs if primer_pairs is not None else []
         self.pps_classified = {}
         self.pps_pruned = {}
@@ -323,6 +342,27 @@ def add_mutations_batch(pcrs, mutations_per_pcr, device=None):
         for c, d in enumerate(order):
             pp.primers[d].max_aaf = max(pp.primers[d].max_aaf, float(aaf[k, c]))
         pp.max_indel_size = max(pp.max_indel_size, int(indel[k]))
+
+
+def add_mutation_strings(pp, mutations):
+    """String half of PrimerPair.add_mutations (reference lib_primer3.py:166-199): per primer the
+    mutation labels 'REFposALT1/ALT2:aaf' and the IUPAC-ambiguous sequence.  R primers (and the ALT
+    primer of an R-direction KASP pair) are handled on the forward strand and flipped back."""
+    for d, p in pp.primers.items():
+        flip = d == "R" or (d == "A" and pp.dir == "R")
+        fwd = lib_utils.reverse_complement(p.sequence) if flip else p.sequence
+        variants = [fwd]
+        for m in mutations:
+            if p.start <= m.pos <= p.stop:
+                base = list(fwd)
+                ppos = m.pos - p.start
+                for malt in m.alt:
+                    base[ppos:(ppos + len(m.ref))] = list(malt)     # edits accumulate, as in the reference
+                    if len(base) == len(fwd):
+                        variants.append("".join(base))
+                p.mutations.append("{}{:d}{}:{}".format(m.ref, m.pos, "/".join(m.alt), lib_utils.round_tidy(m.aaf, 2)))
+        amb = lib_utils.seqs2ambiguous_dna(variants)
+        p.sequence_ambiguous = lib_utils.reverse_complement(amb) if flip else amb
 
 
 def hrm_temps_batch(ref_products, alt_products, device=None):

@@ -37,3 +37,26 @@ def round_tidy(x, n):
     if y <= sys.float_info.min:
         return 0.0
     return np.round(x, int(n - np.ceil(np.log10(y))))
+
+
+# Biopython IUPACData.ambiguous_dna_values, inverted as the reference does (lib_utils.py:15-18)
+_IUPAC_DNA = {"A": "A", "C": "C", "G": "G", "T": "T", "M": "AC", "R": "AG", "W": "AT", "S": "CG", "Y": "CT",
+              "K": "GT", "V": "ACG", "H": "ACT", "D": "AGT", "B": "CGT", "X": "GATC", "N": "GATC"}
+IUPAC_DNA_I = {v: k for k, v in _IUPAC_DNA.items()}
+
+
+def seqs2ambiguous_dna(seqs):
+    """Same-length sequences -> one IUPAC-ambiguous sequence (reference lib_utils.py:216-230);
+    a column whose letter set has no code (e.g. all four bases, whose table key is 'GATC') is N."""
+    out = []
+    for column in zip(*seqs):
+        out.append(IUPAC_DNA_I.get("".join(sorted(set(column))), "N"))
+    return "".join(out)
+
+
+_COMP = str.maketrans("ACGTUacgtuRYKMBVDHrykmbvdhNnSsWw", "TGCAAtgcaaYRMKVBHDyrmkvbhdNnSsWw")
+
+
+def reverse_complement(seq):
+    """Bio.Seq.reverse_complement for (ambiguous) DNA strings."""
+    return seq[::-1].translate(_COMP)

@@ -362,9 +362,43 @@ def golden_design(rng):
         n1 = len(canned)
         repo = lk.design_primers(pps_repo=repo, mpps=mpps, roi=hroi, sequence_excluded_region=[[0, 5]],
                                  n_primers=14)
+        second = [_pp_row(pp) for pp in repo]
+        # the rest of _lib_kasp.main (:739-748) on that repository: dyes, heterodimers, mutations,
+        # classify, prune, report
+        import tempfile
+        covered = sorted({int(p) for pp in repo for d in "FR" for p in range(pp.primers[d].start, pp.primers[d].stop + 1)})
+        muts = []
+        for k, pos in enumerate(rng.choice(covered, size=7, replace=False)):
+            pos = int(pos)
+            r0 = seq[pos - start]
+            alts = [b for b in "ACGT" if b != r0]
+            if k == 2:
+                m = types.SimpleNamespace(pos=pos, ref=r0, alt=alts[:2], aaf=0.31, indel_size=0)
+            elif k == 4:
+                m = types.SimpleNamespace(pos=pos, ref=seq[pos - start:pos - start + 2], alt=[alts[0]], aaf=0.07,
+                                          indel_size=1)
+            else:
+                m = types.SimpleNamespace(pos=pos, ref=r0, alt=[alts[k % 3]], aaf=float(rng.random() * 0.5),
+                                          indel_size=0)
+            muts.append(m)
+        pcr = lk.PCR(snp_id="mk%d" % len(kasp_cases), chrom="chrT", pos=hroi.marker.pos1, ref=ref, alt=alt)
+        pcr.pps = repo
+        pcr.add_reporter_dyes([VIC, FAM])
+        pcr.check_heterodimerization()
+        pcr.add_mutations(muts)
+        pcr.classify(assay_name="KASP")
+        n_kept = pcr.prune(6)
+        pcr.is_indel = None
+        with tempfile.TemporaryDirectory() as tmp:
+            lk.print_report(pcr, os.path.join(tmp, "rep"))
+            lk.print_report_header(os.path.join(tmp, "hdr.txt"))
+            report = {k: open(os.path.join(tmp, k)).read() for k in ("rep.txt", "rep.bed", "hdr.txt")}
         kasp_cases.append({"seq": seq, "start": start, "stop": hroi.stop, "pos1": hroi.marker.pos1, "ref": ref,
                            "alt": alt, "excluded": [excluded, [[0, 5]]], "n_primers": [10, 14],
-                           "canned": [canned[:n1], canned[n1:]], "repo": [first, [_pp_row(pp) for pp in repo]]})
+                           "canned": [canned[:n1], canned[n1:]], "repo": [first, second],
+                           "mutations": [{"pos": m.pos, "ref": m.ref, "alt": m.alt, "aaf": m.aaf,
+                                          "indel_size": m.indel_size} for m in muts],
+                           "n_kept": int(n_kept), "report": report})
     # PCR: both primers picked, diversity limit max_unique = 2
     pcr_cases = []
     for _ in range(2):

@@ -79,6 +79,25 @@ def test_kasp_design_primers_matches_reference(monkeypatch):
                 assert args[key] == mpp.primers[mpp.dir].sequence and args["SEQUENCE_TEMPLATE"] == case["seq"]
                 assert [list(x) for x in args["SEQUENCE_EXCLUDED_REGION"]] == excluded
             assert [row_of(pp) for pp in repo] == want
+        # the rest of _lib_kasp.main on that repository: dyes, heterodimers, mutations, classify,
+        # prune and the report writer -- byte-identical to the files the reference wrote
+        from helpers import VIC, FAM
+        muts = [types.SimpleNamespace(**m) for m in case["mutations"]]
+        pcr_ = kasp.PCR(snp_id="mk%d" % fx["kasp"].index(case), chrom="chrT", pos=case["pos1"], ref=case["ref"],
+                        alt=case["alt"])
+        pcr_.pps = repo
+        pcr_.add_reporter_dyes([VIC, FAM])
+        lp.add_mutations_batch([pcr_], [muts])
+        for pp in pcr_.pps:
+            lp.add_mutation_strings(pp, muts)
+        lp.rank_batch([pcr_], 6, "KASP", reporters=(VIC, FAM))
+        assert sum(len(v) for v in pcr_.pps_pruned.values()) == case["n_kept"]
+        import tempfile
+        with tempfile.TemporaryDirectory() as tmp:
+            kasp.print_report(pcr_, os.path.join(tmp, "rep"))
+            kasp.print_report_header(os.path.join(tmp, "hdr.txt"))
+            for name in ("rep.txt", "rep.bed", "hdr.txt"):
+                assert open(os.path.join(tmp, name)).read() == case["report"][name], name
 
 
 @pytest.mark.gpu

@@ -147,3 +147,23 @@ def test_two_rank_gloo_shard_and_gather():
         assert p.exitcode == 0
     assert units == list(range(101))
     assert scores == [u * 2.5 for u in range(101)]
+
+
+def test_ambiguous_sequences_and_mutation_labels():
+    # string half of PrimerPair.add_mutations (reference lib_primer3.py:166-199) on hand-checked cases
+    import types
+    from polyoligo_b200 import lib_primer3 as lp, lib_utils
+    assert lib_utils.seqs2ambiguous_dna(["ACGT", "ACGA", "TCGT"]) == "WCGW"
+    assert lib_utils.seqs2ambiguous_dna(["A", "C", "G", "T"]) == "N"       # 'ACGT' is not a key of the inverted table
+    assert lib_utils.reverse_complement("ACGTRYKM") == "KMRYACGT"
+    pp = lp.PrimerPair()
+    pp.dir = None
+    pp.primers["F"] = lp.Primer(sequence="ACGTACGTAC", start=100, stop=109)
+    pp.primers["R"] = lp.Primer(sequence="GGGTTTCCCA", start=200, stop=209)   # reverse strand: TGGGAAACCC on the template
+    muts = [types.SimpleNamespace(pos=102, ref="G", alt=["A"], aaf=0.25, indel_size=0),
+            types.SimpleNamespace(pos=200, ref="T", alt=["C", "G"], aaf=0.125, indel_size=3),
+            types.SimpleNamespace(pos=150, ref="A", alt=["T"], aaf=0.4, indel_size=7)]
+    pp.add_mutations(muts)
+    assert pp.primers["F"].sequence_ambiguous == "ACRTACGTAC" and pp.primers["F"].mutations == ["G102A:0.25"]
+    assert pp.primers["R"].sequence_ambiguous == "GGGTTTCCCV" and pp.primers["R"].mutations == ["T200C/G:0.12"]
+    assert (pp.primers["F"].max_aaf, pp.primers["R"].max_aaf, pp.max_indel_size) == (0.25, 0.125, 7)
