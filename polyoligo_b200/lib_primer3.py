@@ -18,12 +18,42 @@ from .thermoanalysis import get_context, gc_content
 
 PRIMER3_GLOBALS = {}     # the PRIMER_* thresholds of the assay YAML (reference data/PRIMER3_*.yaml)
 TM_DELTA = 5             # reference lib_primer3.py:21
+MIN_OFFTARGET_SIZE = 0   # reference lib_primer3.py:17-18 (set_offtarget_size)
+MAX_OFFTARGET_SIZE = 1000
 
 
 def set_globals(**kwargs):
     """reference lib_primer3.py:539-544: remembers the tags and hands them to the primer picker."""
     PRIMER3_GLOBALS.update(kwargs)
     primer3_bindings.setP3Globals(PRIMER3_GLOBALS)
+
+
+def set_offtarget_size(min_size, max_size):
+    global MIN_OFFTARGET_SIZE, MAX_OFFTARGET_SIZE
+    MIN_OFFTARGET_SIZE, MAX_OFFTARGET_SIZE = min_size, max_size
+
+
+def list_offtargets(pp_hits):
+    """Off-target PCR products of one primer pair from its BLAST hits (reference
+    lib_primer3.py:392-419; BLAST itself stays external): pp_hits[d][chrom] is a list of hits
+    with 'sstart'.  Per chromosome the distinct forward starts i and reverse starts j are sorted;
+    for each i the stops j > i are walked in order and reported while MIN < j - i < MAX -- the
+    walk STOPS at the first j > i outside that range, also when it is still too close (the
+    reference's `else: break`), which is kept."""
+    out = []
+    for chrom in pp_hits["F"]:
+        if chrom not in pp_hits["R"]:
+            continue
+        starts = np.unique([h["sstart"] for h in pp_hits["F"][chrom]])
+        stops = np.unique([h["sstart"] for h in pp_hits["R"][chrom]])
+        for i in starts:
+            for j in stops[np.searchsorted(stops, i, side="right"):]:
+                delta = j - i
+                if MIN_OFFTARGET_SIZE < delta < MAX_OFFTARGET_SIZE:
+                    out.append("{}:{}-{}".format(chrom, i, j))
+                else:
+                    break
+    return out
 
 
 def set_tm_delta(v):

@@ -277,6 +277,22 @@ def golden_mutations(rng):
     dump("mutations.json", {"cases": cases})
 
 
+def golden_offtargets(rng):
+    """8f-4: PCR.list_offtargets (reference lib_primer3.py:392-419) on random BLAST-like hits."""
+    lp.set_offtarget_size(40, 900)
+    cases = []
+    for _ in range(12):
+        hits = {"F": {}, "R": {}}
+        for d in "FR":
+            # sorted: dump() writes dict keys sorted, and the iteration order decides the output order
+            for chrom in sorted(rng.choice(["chr1", "chr2", "chr3", "scaffold_9"], size=int(rng.integers(1, 5)),
+                                           replace=False)):
+                n = int(rng.integers(0, 9))
+                hits[d][str(chrom)] = [{"sstart": int(x)} for x in rng.integers(1000, 3000, n)]
+        cases.append({"hits": hits, "offtargets": lp.PCR.list_offtargets(hits)})
+    dump("offtargets.json", {"min_size": 40, "max_size": 900, "cases": cases})
+
+
 def _p3_dict(pairs):
     """primer3-py style result dict (key order as primer3 emits it) from oracle picker pairs."""
     d = {"PRIMER_LEFT_EXPLAIN": "considered 0", "PRIMER_RIGHT_EXPLAIN": "considered 0",
@@ -416,6 +432,9 @@ def golden_design(rng):
 
 
 if __name__ == "__main__":
+    if "--offtargets-only" in sys.argv:
+        golden_offtargets(np.random.default_rng(20240611))
+        sys.exit(0)
     if "--design-only" in sys.argv:
         golden_design(np.random.default_rng(20240610))
         sys.exit(0)
@@ -427,3 +446,4 @@ if __name__ == "__main__":
     golden_masks(rng)
     golden_mutations(np.random.default_rng(20240609))
     golden_design(np.random.default_rng(20240610))
+    golden_offtargets(np.random.default_rng(20240611))

@@ -167,3 +167,15 @@ def test_ambiguous_sequences_and_mutation_labels():
     assert pp.primers["F"].sequence_ambiguous == "ACRTACGTAC" and pp.primers["F"].mutations == ["G102A:0.25"]
     assert pp.primers["R"].sequence_ambiguous == "GGGTTTCCCV" and pp.primers["R"].mutations == ["T200C/G:0.12"]
     assert (pp.primers["F"].max_aaf, pp.primers["R"].max_aaf, pp.max_indel_size) == (0.25, 0.125, 7)
+
+
+def test_list_offtargets_matches_reference_fixture():
+    import json, os
+    from polyoligo_b200 import lib_primer3 as lp
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "offtargets.json")))
+    lp.set_offtarget_size(fx["min_size"], fx["max_size"])
+    n = 0
+    for case in fx["cases"]:
+        assert lp.list_offtargets(case["hits"]) == case["offtargets"]
+        n += len(case["offtargets"])
+    assert n > 20
