@@ -311,7 +311,13 @@ def run_b200(args, rank, world, local_rank):
                     "peak_source": "measured here: register-resident DFMA microbenchmark (po_measure_fp64_peak)",
                     "relaxations_per_launch": relax_het, "flop_per_relaxation": FLOP_PER_RELAXATION,
                     "kernel_ms": het_ms, "share_of_step": het_ms / (dev_ms / args.steps),
-                    "traffic": None,
+                    # ncu --set full, 400k-pair launch of this kernel: dram__bytes_read.sum 12.916 MB +
+                    # dram__bytes_write.sum 0.007 MB (profiles/r1_v6_ncu_full_summary.txt) = 32.3 B per
+                    # pair, i.e. the two 16-byte input records; scaled to this launch's pair count
+                    "traffic": 32.31 * n,
+                    "traffic_note": "DRAM bytes per launch scaled from the ncu capture of a 400k-pair launch "
+                                    "(32.3 B/pair: inputs only, results stay in L2 within the capture); "
+                                    "algorithmic bytes are 72 B/pair (32 in + 40 out)",
                     "hbm": {"achieved_gbs": hbm_bytes / (het_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                             "frac": hbm_bytes / (het_ms * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
