@@ -480,16 +480,6 @@ extern "C" int po_sync(po_ctx* ctx, void* stream) {
 }
 
 // ---- host-buffer entry points -------------------------------------------------
-static int pinned(po_ctx* ctx, DevBuf& buf, size_t bytes) {
-    if (bytes <= buf.cap) return PO_OK;
-    if (buf.p) CK(cudaFreeHost(buf.p));
-    buf.p = nullptr;
-    buf.cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    CK(cudaMallocHost(&buf.p, want));
-    buf.cap = want;
-    return PO_OK;
-}
 
 extern "C" int po_tm_batch(po_ctx* ctx, const po_oligo* oligos, int64_t n, double* tm, double* gc) {
     if (!ctx || !oligos || !tm || n < 0) return PO_E_INVALID;
