@@ -348,6 +348,13 @@ def run_b200(args, rank, world, local_rank):
             ref = orc.thal_batch(synth.to_strings(a_np[:20000]), synth.to_strings(b_np[:20000]), 1, nthreads=threads)
             got = out_np["het"][:20000]
             parity = bool(np.array_equal(got["tm"], ref["tm"]) and np.array_equal(got["dg"], ref["dg"]))
+            if c5 is not None and c5["thal_evaluations_rank0"] > 0:
+                # not a measurement: the picker's own thal work at the CPU oracle's measured rate
+                cpu_rate = EVALS_PER_PAIR * args.cpu_sample / dt
+                c5["cpu_estimate_markers_per_s"] = cpu_rate / (c5["thal_evaluations_rank0"] / args.markers)
+                c5["cpu_estimate_note"] = ("ESTIMATE: thal evaluations per marker of this run divided into the "
+                                           "oracle's measured config-4 thal rate on %d cores; enumeration, "
+                                           "sorting and ranking not counted" % threads)
             line["cpu_baseline"] = {"value": EVALS_PER_PAIR * args.cpu_sample / dt, "unit": UNIT, "cores": threads,
                                     "kind": "port",
                                     "sample": "config-4 batch of %d pairs, one pass (same generator, smaller n)" % args.cpu_sample,
