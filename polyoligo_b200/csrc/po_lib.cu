@@ -42,8 +42,16 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
 // exceeds CAP are appended to `overflow` and picked up by the large-CAP pass.
 //   list == nullptr : items are 0..n-1
 //   list != nullptr : items are list[0 .. *list_n)
+// warps per CTA of the first-tier kernels (2 CTAs per SM; 72 registers per thread).  Measured
+// on B200 (3M config-4 pairs): 13 / 14 warps 227.3 / 206.8 ms vs 12 / 12 warps 229.4 / 210.2 ms.
+#ifndef PO_DIMER_WARPS
+#define PO_DIMER_WARPS 13
+#endif
+#ifndef PO_HAIRPIN_WARPS
+#define PO_HAIRPIN_WARPS 14
+#endif
 template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS >= 12 ? 2 : 1))
 k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po_thal_out* __restrict__ out,
        const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
        const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
@@ -432,7 +440,7 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
     const int cap = ctx->fast_cap;
     if (type == PO_THAL_HAIRPIN) {
         if (cap == 256) rc = launch_thal<256, 12, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
-        else rc = launch_thal<128, 12, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+        else rc = launch_thal<128, PO_HAIRPIN_WARPS, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
         if (rc) return rc;
         return launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx);
     }
@@ -448,7 +456,7 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
     }
     if (cap == 192) rc = launch_thal<192, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
     else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
-    else rc = launch_thal<256, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
+    else rc = launch_thal<256, PO_DIMER_WARPS, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
     if (rc) return rc;
     if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em, out2))) return rc;
     return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em, out2);
