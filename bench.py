@@ -44,7 +44,7 @@ def parse():
     p.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
     p.add_argument("--cpu-sample", type=int, default=150_000, help="pairs in the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--markers", type=int, default=2048,
+    p.add_argument("--markers", type=int, default=8192,
                    help="markers per GPU of the secondary config-5 (KASP design) measurement; 0 skips it")
     return p.parse_args()
 
@@ -146,7 +146,6 @@ def run_config5(args, rank, local_rank, barrier):
     merge, reporter-tailed heterodimers, goodness, top-10) of synthetic markers through the public
     array API with HOST buffers; wall clock of one pass after a small warm-up."""
     from polyoligo_b200 import kasp_pipeline as kp, lib_primer3 as lp, primer3_bindings as p3b
-    from polyoligo_b200.thermoanalysis import get_context
     p3b.resetP3Globals()
     lp.PRIMER3_GLOBALS.clear()
     # reference src/polyoligo/data/PRIMER3_KASP.yaml + cli_kasp.py defaults (--depth 100, -n 10, dyes)
@@ -157,21 +156,26 @@ def run_config5(args, rank, local_rank, barrier):
                    PRIMER_PRODUCT_SIZE_RANGE=[[90, 150], [100, 200], [50, 250]], PRIMER_NUM_RETURN=100)
     lp.set_tm_delta(5.0)
     dyes = ("GAAGGTCGGAGTCAACGGATT", "GAAGGTGACCAAGTTCATGCT")
-    kctx = get_context(local_rank)
-    kp.design_markers_arrays(kp.synth_config5(args.markers, seed=1), n_primers=10, reporters=dyes, device=local_rank)  # warm-up
+    workers = 2
+    kctxs = [kp._worker_context(local_rank, slot) for slot in range(workers)]
+    kp.design_markers_arrays(kp.synth_config5(args.markers, seed=1), n_primers=10, reporters=dyes, device=local_rank,
+                             workers=2)  # warm-up
     data = kp.synth_config5(args.markers, seed=kp.CONFIG5_SEED + rank)
     stats = {}
-    items0, launches0 = kctx.thal_item_count(), kctx.launch_count()
+    items0 = sum(c.thal_item_count() for c in kctxs)
+    launches0 = sum(c.launch_count() for c in kctxs)
     barrier()
     t0 = time.perf_counter()
-    res = kp.design_markers_arrays(data, n_primers=10, reporters=dyes, device=local_rank, stats=stats)
+    res = kp.design_markers_arrays(data, n_primers=10, reporters=dyes, device=local_rank, stats=stats,
+                                   workers=workers)
     dt = time.perf_counter() - t0
     barrier()
     c5 = {"workload": "synthetic KASP design, %d markers per GPU x 500 nt, SNP at 249, depth 100, top 10, "
                       "no off-targets (BASELINE config 5 shape)" % args.markers,
           "timing": "host wall clock of one pass through kasp_pipeline.design_markers_arrays (host buffers)",
-          "thal_evaluations_rank0": int(kctx.thal_item_count() - items0),
-          "gpu_launches": int(kctx.launch_count() - launches0),
+          "thal_evaluations_rank0": int(sum(c.thal_item_count() for c in kctxs) - items0),
+          "gpu_launches": int(sum(c.launch_count() for c in kctxs) - launches0),
+          "host_threads": workers,
           "picker_tasks": int(stats.get("p3_tasks", 0)), "picker_pairs": int(stats.get("p3_pairs", 0)),
           "markers_with_pairs": int((res["n_sel"] > 0).sum()), "pairs_ranked": int(len(res["f"]))}
     return c5, dt * 1e3

@@ -19,10 +19,33 @@ indels <= 32 nt, the given marker primer is taken at its true template position 
 reference's designPrimers locates it with a string search, which is the same position unless
 the primer occurs twice in the template), and BLAST off-targets are fixed to none.
 """
+import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
 
 from . import _native, lib_primer3, primer3_bindings
 from .thermoanalysis import get_context
+
+_worker_contexts = {}
+_worker_lock = threading.Lock()
+
+
+def _worker_context(device, slot):
+    """One scoring context per (process, device, worker slot): chunks are processed by a few host
+    threads so that one chunk's numpy glue overlaps another chunk's kernels (the C calls release
+    the GIL)."""
+    if slot == 0:
+        return get_context(device)
+    base = get_context(device)
+    key = (os.getpid(), base.device, slot)
+    with _worker_lock:
+        ctx = _worker_contexts.get(key)
+        if ctx is None:
+            ctx = _native.Context(base.device)
+            _worker_contexts[key] = ctx
+        return ctx
 
 CONFIG5_SEED = 20240608
 _LETTERS = np.frombuffer(b"ACGT", dtype=np.uint8)
@@ -107,12 +130,11 @@ def _slot_geometry(marker_idx, ref_len, alt_len, length, lo, hi):
     return start.astype(np.int32), ln.astype(np.int32)
 
 
-def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk=2048, stats=None):
+def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk=2048, stats=None, workers=2):
     """Runs the pipeline on a marker set laid out like synth_config5()'s result.  Thresholds come
     from lib_primer3.PRIMER3_GLOBALS / TM_DELTA and primer3_bindings' globals (set_globals).
     Returns per-marker arrays: ``sel`` (n, n_primers) indices into the merged pair arrays
     ``f`` / ``r`` / ``a`` (oligo records), ``dir``, ``goodness``, ``qbits``, ``seg``."""
-    ctx = get_context(device)
     g = lib_primer3.PRIMER3_GLOBALS
     lo, hi = int(g["PRIMER_MIN_SIZE"]), int(g["PRIMER_MAX_SIZE"])
     settings = primer3_bindings.settings_from_globals()
@@ -123,12 +145,34 @@ def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk
     out = {k: [] for k in ("f", "r", "a", "dir", "goodness", "qbits", "sel", "n_sel", "count")}
     types_ = ["mism_mut", "mism", "partial_mism_mut", "partial_mism", "all_mut", "all"] \
         if data.get("mut_seg") is not None else ["mism", "partial_mism", "all"]
-    for c0 in range(0, n, chunk):
-        c1 = min(n, c0 + chunk)
-        res = _design_chunk(ctx, data, c0, c1, templates[c0:c1], length, lo, hi, settings, depth, vparams, types_,
-                            n_primers, reporters, stats)
+    bounds = [(c0, min(n, c0 + chunk)) for c0 in range(0, n, chunk)]
+    workers = max(1, min(workers, len(bounds)))
+    slots = list(range(workers))
+    slot_lock = threading.Lock()
+
+    def run(b):
+        with slot_lock:
+            slot = slots.pop()
+        try:
+            st = {} if stats is not None else None
+            res = _design_chunk(_worker_context(device, slot), data, b[0], b[1], templates[b[0]:b[1]], length, lo, hi,
+                                settings, depth, vparams, types_, n_primers, reporters, st)
+            return res, st
+        finally:
+            with slot_lock:
+                slots.append(slot)
+
+    if workers == 1:
+        results = [run(b) for b in bounds]
+    else:
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            results = list(pool.map(run, bounds))
+    for res, st in results:
         for k in out:
             out[k].append(res[k])
+        if stats is not None:
+            for k, v in st.items():
+                stats[k] = stats.get(k, 0) + v
     seg = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.concatenate(out["count"]), out=seg[1:])
     off = 0

@@ -5,6 +5,7 @@ from polyoligo_b200 import kasp_pipeline as kp, lib_primer3 as lp, primer3_bindi
 from polyoligo_b200.thermoanalysis import get_context
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 chunk = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+workers = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 p3b.resetP3Globals(); lp.PRIMER3_GLOBALS.clear()
 lp.set_globals(PRIMER_OPT_SIZE=20, PRIMER_MIN_SIZE=18, PRIMER_MAX_SIZE=25, PRIMER_OPT_TM=60.0, PRIMER_MIN_TM=55.0,
                PRIMER_MAX_TM=65.0, PRIMER_MIN_GC=20.0, PRIMER_MAX_GC=80.0, PRIMER_MAX_POLY_X=100,
@@ -21,11 +22,11 @@ for name in ("kasp_enumerate", "oligo_props_batch", "p3_design_fixed", "annotate
         return w
     setattr(ctx, name, wrap())
 dyes = ("GAAGGTCGGAGTCAACGGATT", "GAAGGTGACCAAGTTCATGCT")
-kp.design_markers_arrays(kp.synth_config5(n, seed=1), n_primers=10, reporters=dyes, chunk=chunk)   # same-size warm-up
+kp.design_markers_arrays(kp.synth_config5(n, seed=1), n_primers=10, reporters=dyes, chunk=chunk, workers=workers)   # same-size warm-up
 T.clear()
 data = kp.synth_config5(n)
 t0 = time.perf_counter()
-res = kp.design_markers_arrays(data, n_primers=10, reporters=dyes, chunk=chunk)
+res = kp.design_markers_arrays(data, n_primers=10, reporters=dyes, chunk=chunk, workers=workers)
 tot = time.perf_counter() - t0
 print("total %.3f s  %.0f markers/s" % (tot, n / tot))
 for k, v in T.items(): print("  %-22s %.3f s" % (k, v))
