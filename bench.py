@@ -44,6 +44,7 @@ def parse():
     p.add_argument("--pairs", type=int, default=10_000_000, help="pairs per GPU per step")
     p.add_argument("--cpu-sample", type=int, default=150_000, help="pairs in the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-markers", type=int, default=64, help="markers in the config-5 CPU baseline sample")
     p.add_argument("--markers", type=int, default=8192,
                    help="markers per GPU of the secondary config-5 (KASP design) measurement; 0 skips it")
     return p.parse_args()
@@ -352,13 +353,21 @@ def run_b200(args, rank, world, local_rank):
             ref = orc.thal_batch(synth.to_strings(a_np[:20000]), synth.to_strings(b_np[:20000]), 1, nthreads=threads)
             got = out_np["het"][:20000]
             parity = bool(np.array_equal(got["tm"], ref["tm"]) and np.array_equal(got["dg"], ref["dg"]))
-            if c5 is not None and c5["thal_evaluations_rank0"] > 0:
-                # not a measurement: the picker's own thal work at the CPU oracle's measured rate
-                cpu_rate = EVALS_PER_PAIR * args.cpu_sample / dt
-                c5["cpu_estimate_markers_per_s"] = cpu_rate / (c5["thal_evaluations_rank0"] / args.markers)
-                c5["cpu_estimate_note"] = ("ESTIMATE: thal evaluations per marker of this run divided into the "
-                                           "oracle's measured config-4 thal rate on %d cores; enumeration, "
-                                           "sorting and ranking not counted" % threads)
+            if c5 is not None and args.cpu_markers > 0:
+                # the same pipeline with the CPU oracle's context (C-oracle thal on all cores, lazy picker)
+                from oracle.cpu_pipeline import CpuContext
+                from polyoligo_b200 import kasp_pipeline as kp
+                cdata = kp.synth_config5(args.cpu_markers, seed=kp.CONFIG5_SEED)
+                cctx = CpuContext(nthreads=threads)
+                t0 = time.perf_counter()
+                cres = kp.design_markers_arrays(cdata, n_primers=10, ctx=cctx,
+                                                reporters=("GAAGGTCGGAGTCAACGGATT", "GAAGGTGACCAAGTTCATGCT"))
+                cdt = time.perf_counter() - t0
+                c5["cpu_baseline"] = {"value": args.cpu_markers / cdt, "unit": "markers/s", "cores": threads,
+                                      "kind": "port", "thal_evaluations": int(cctx.thal_item_count()),
+                                      "pairs_ranked": int(len(cres["f"])),
+                                      "sample": "first %d markers of the same generator, one pass of the same "
+                                                "pipeline through oracle/cpu_pipeline.py" % args.cpu_markers}
             line["cpu_baseline"] = {"value": EVALS_PER_PAIR * args.cpu_sample / dt, "unit": UNIT, "cores": threads,
                                     "kind": "port",
                                     "sample": "config-4 batch of %d pairs, one pass (same generator, smaller n)" % args.cpu_sample,

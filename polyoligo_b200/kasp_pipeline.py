@@ -130,9 +130,12 @@ def _slot_geometry(marker_idx, ref_len, alt_len, length, lo, hi):
     return start.astype(np.int32), ln.astype(np.int32)
 
 
-def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk=2048, stats=None, workers=2):
+def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk=2048, stats=None, workers=2,
+                          ctx=None):
     """Runs the pipeline on a marker set laid out like synth_config5()'s result.  Thresholds come
     from lib_primer3.PRIMER3_GLOBALS / TM_DELTA and primer3_bindings' globals (set_globals).
+    ``ctx`` replaces the scoring context (tests and the bench's CPU baseline inject the CPU
+    oracle's context there; the product never does).
     Returns per-marker arrays: ``sel`` (n, n_primers) indices into the merged pair arrays
     ``f`` / ``r`` / ``a`` (oligo records), ``dir``, ``goodness``, ``qbits``, ``seg``."""
     g = lib_primer3.PRIMER3_GLOBALS
@@ -146,7 +149,7 @@ def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk
     types_ = ["mism_mut", "mism", "partial_mism_mut", "partial_mism", "all_mut", "all"] \
         if data.get("mut_seg") is not None else ["mism", "partial_mism", "all"]
     bounds = [(c0, min(n, c0 + chunk)) for c0 in range(0, n, chunk)]
-    workers = max(1, min(workers, len(bounds)))
+    workers = 1 if ctx is not None else max(1, min(workers, len(bounds)))
     slots = list(range(workers))
     slot_lock = threading.Lock()
 
@@ -155,7 +158,8 @@ def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk
             slot = slots.pop()
         try:
             st = {} if stats is not None else None
-            res = _design_chunk(_worker_context(device, slot), data, b[0], b[1], templates[b[0]:b[1]], length, lo, hi,
+            res = _design_chunk(ctx if ctx is not None else _worker_context(device, slot), data, b[0], b[1],
+                                templates[b[0]:b[1]], length, lo, hi,
                                 settings, depth, vparams, types_, n_primers, reporters, st)
             return res, st
         finally:

@@ -168,3 +168,30 @@ def test_array_pipeline_matches_object_pipeline():
         total += len(want_repo)
     assert total > 30
     p3b.resetP3Globals()
+
+
+@pytest.mark.gpu
+def test_array_pipeline_matches_cpu_oracle_pipeline():
+    # the whole config-5 pipeline, GPU context against the CPU oracle context (oracle/cpu_pipeline.py:
+    # C-oracle thermodynamics, lazy picker, Python scoring), reference defaults (depth 100, top 10)
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from oracle.cpu_pipeline import CpuContext
+    from polyoligo_b200 import kasp_pipeline as kp
+    from helpers import VIC, FAM
+    lp.PRIMER3_GLOBALS.clear()
+    p3b.resetP3Globals()
+    lp.set_globals(PRIMER_OPT_SIZE=20, PRIMER_MIN_SIZE=18, PRIMER_MAX_SIZE=25, PRIMER_OPT_TM=60.0, PRIMER_MIN_TM=55.0,
+                   PRIMER_MAX_TM=65.0, PRIMER_MIN_GC=20.0, PRIMER_MAX_GC=80.0, PRIMER_MAX_POLY_X=100,
+                   PRIMER_SALT_MONOVALENT=50.0, PRIMER_DNA_CONC=50.0, PRIMER_PAIR_MAX_DIFF_TM=6.0,
+                   PRIMER_PRODUCT_SIZE_RANGE=[[90, 150], [100, 200], [50, 250]], PRIMER_NUM_RETURN=100)
+    lp.set_tm_delta(5.0)
+    data = kp.synth_config5(12, seed=31)
+    gpu = kp.design_markers_arrays(data, n_primers=10, reporters=(VIC, FAM), chunk=5)
+    cpu = kp.design_markers_arrays(data, n_primers=10, reporters=(VIC, FAM), chunk=5, ctx=CpuContext(nthreads=8))
+    assert len(gpu["f"]) == len(cpu["f"]) > 100
+    for k in ("seg", "dir", "goodness", "qbits", "sel", "n_sel"):
+        assert np.array_equal(gpu[k], cpu[k]), k
+    for k in ("f", "r", "a"):
+        assert gpu[k].tobytes() == cpu[k].tobytes(), k
+    p3b.resetP3Globals()
