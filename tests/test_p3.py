@@ -264,3 +264,53 @@ def test_fixed_primer_design_depth_100_and_ties(ctx, oracle):
             _check_pairs(_rows_for_task(fixed, pairs, n_pairs, tasks, i), ref, "depth %d task %d" % (depth, i))
             n_checked += len(ref)
     assert n_checked > 150
+
+
+@pytest.mark.gpu
+def test_picker_edge_cases(ctx, oracle):
+    rng = np.random.default_rng(2)
+    s = _gpu_settings(4)
+    # no templates, empty / too short / fully masked templates, template with N
+    lo, recs = ctx.p3_candidates(s, [])
+    assert list(lo) == [0] and len(recs) == 0
+    t_ok = rand_template(rng, 120)
+    templates = ["", "ACGTACGTAC", t_ok, t_ok, "N" * 80]
+    masks = [np.zeros(len(t), np.uint8) for t in templates]
+    masks[3][:] = 1
+    lo, recs = ctx.p3_candidates(s, templates, masks)
+    per_list = np.diff(lo)
+    assert per_list[0] == per_list[1] == per_list[2] == per_list[3] == 0       # sets 0 and 1
+    assert per_list[4] > 0 and per_list[5] > 0                                   # the plain template
+    assert per_list[6] == per_list[7] == per_list[8] == per_list[9] == 0       # masked, all-N
+    # tasks: primer outside the template, wrong length, on masked bases, no tasks at all
+    tasks = np.array([(2, 1, 110, 20), (2, 1, 10, 5), (3, 1, 10, 20), (2, 2, 5, 20), (2, 3, 10, 20)],
+                     dtype=_native.P3_TASK_DTYPE)
+    fixed, pairs, n_pairs = ctx.p3_design_fixed(s, templates, tasks, masks)
+    assert not (fixed["flags"] & _native.P3_OK).any() and not n_pairs.any()
+    f0, p0, n0 = ctx.p3_design_fixed(s, templates, np.zeros(0, dtype=_native.P3_TASK_DTYPE), masks)
+    assert len(f0) == 0 and p0.shape == (0, 4)
+    with pytest.raises(RuntimeError):
+        ctx.p3_design_fixed(s, templates, np.array([(9, 1, 0, 20)], dtype=_native.P3_TASK_DTYPE), masks)
+    # a target between the given primer and the picked ones, and an included region (two-sided call)
+    p3b.resetP3Globals()
+    g = {**KASP_GLOBALS, "PRIMER_NUM_RETURN": 6, "PRIMER_PRODUCT_SIZE_RANGE": [[60, 170]]}
+    p3b.setP3Globals(g)
+    so = oracle_settings(g, 6)
+    t = rand_template(rng, 200)
+    full = {**p3_oracle.DEFAULTS, **so}
+    for left in [r for r in p3_oracle.candidates(full, t, [0] * len(t), "L")
+                 if r["start"] >= 30 and r["start"] + r["len"] <= 88]:
+        ref = p3_oracle.design(oracle, so, t, target=(90, 10), left=left["seq"])
+        if ref:       # skip given primers whose own self alignments exceed the limits
+            break
+    res = p3b.designPrimers({"SEQUENCE_TEMPLATE": t, "SEQUENCE_PRIMER": left["seq"], "SEQUENCE_TARGET": [90, 10]})
+    assert res["PRIMER_PAIR_NUM_RETURNED"] == len(ref) > 0
+    for i, e in enumerate(ref):
+        assert res["PRIMER_RIGHT_%d_SEQUENCE" % i] == e["right"]["seq"]
+        assert e["right"]["start"] - e["right"]["len"] + 1 >= 100
+    res = p3b.designPrimers({"SEQUENCE_TEMPLATE": t, "SEQUENCE_INCLUDED_REGION": [20, 150]})
+    ref = p3_oracle.design(oracle, so, t, excluded=[(0, 20), (170, 30)])
+    assert res["PRIMER_PAIR_NUM_RETURNED"] == len(ref) > 0
+    assert [res["PRIMER_LEFT_%d_SEQUENCE" % i] for i in range(len(ref))] == [e["left"]["seq"] for e in ref]
+    assert [res["PRIMER_RIGHT_%d" % i] for i in range(len(ref))] == [(e["right"]["start"], e["right"]["len"]) for e in ref]
+    p3b.resetP3Globals()
