@@ -13,8 +13,9 @@ libprimer3 is third-party code that is not in the reference tree; what is
 implemented here is the restatement described in DESIGN.md section 7 (parity
 with the real library UNPINNED).  Candidate enumeration, sorting, the
 fixed-primer search and every thermodynamic alignment run on the GPU; the
-two-sided pair search walks the sorted lists on the host and batches its
-alignments to the GPU.
+two-sided search (both primers picked) turns the best left candidates of every
+template into fixed-primer tasks of one device call and merges their answers on
+the host under an exactness bound (_search_two_sided_batch).
 
 ``designPrimers`` returns a primer3-py style dict (``PRIMER_LEFT_0_SEQUENCE``,
 ``PRIMER_PAIR_0_PENALTY``, ...), so ``lib_primer3.get_primers`` parses it
@@ -309,6 +310,67 @@ def _search_two_sided(ctx, s, L, R, target):
     return accepted
 
 
+def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_penalty):
+    """Both primers picked, for many templates at once, on top of the device's fixed-primer search:
+    every one of the best M left candidates of a template becomes a 'left primer given' task (one
+    device call for all templates), and the per-left answers are merged.  Pairs of the left
+    candidates not yet covered have a penalty of at least L[M].penalty + R[0].penalty, so the merge
+    is final once the wanted number of pairs lies strictly below that bound (or every left
+    candidate has been covered); otherwise M grows.  Size ranges are honoured in order: a later
+    range only fills what the earlier ones left open."""
+    n = len(templates)
+    want_total = s.num_return
+    rows = [[] for _ in range(n)]
+    covered = [0] * n
+    result = [None] * n
+    M = 64
+    while any(r is None for r in result):
+        tasks, owner = [], []
+        for t in range(n):
+            if result[t] is not None:
+                continue
+            hi = min(M, len(lefts[t]))
+            for li in range(covered[t], hi):
+                tasks.append((t, 1, int(lefts[t]["start"][li]), int(lefts[t]["len"][li])))
+                owner.append(t)
+            covered[t] = hi
+        if tasks:
+            tasks = np.array(tasks, dtype=_native.P3_TASK_DTYPE)
+            fixed, pairs, n_pairs = ctx.p3_design_fixed(s, templates, tasks, masks, targets)
+            for k, t in enumerate(owner):
+                l = fixed[k]
+                for p in pairs[k, :n_pairs[k]]:
+                    r = p["other"]
+                    cm = (r["self_end_th"] + l["self_end_th"] + p["compl_end_th"]) * 1.1 + r["self_any_th"] + \
+                        l["self_any_th"] + p["compl_any_th"]
+                    key = (float(p["pair_penalty"]), float(cm), -int(l["start"]), int(r["start"]), int(l["len"]),
+                           int(r["len"]))
+                    rows[t].append((int(p["size_range"]), key, l.copy(), r.copy(), p))
+        for t in range(n):
+            if result[t] is not None:
+                continue
+            all_left = covered[t] >= len(lefts[t])
+            bound = np.inf if all_left else float(lefts[t]["penalty"][covered[t]]) + right_min_penalty[t]
+            chosen, complete = [], True
+            for interval in range(s.n_size_ranges):
+                want = want_total - len(chosen)
+                if want <= 0:
+                    break
+                cand = sorted((x for x in rows[t] if x[0] == interval), key=lambda x: x[1])
+                if all_left:
+                    chosen += cand[:want]
+                elif len(cand) >= want and cand[want - 1][1][0] < bound:
+                    chosen += cand[:want]
+                else:
+                    complete = False      # an uncovered left candidate could still enter this range
+                    break
+            if complete:
+                result[t] = [(l, r, p["pair_penalty"], p["compl_any_th"], p["compl_end_th"], p["product_size"])
+                             for _, _, l, r, p in chosen[:want_total]]
+        M *= 4
+    return result
+
+
 # ---- public entry points ------------------------------------------------------------------
 def design_primers_batch(seq_args_list, global_args=None, device=None):
     """designPrimers for many seq_args at once; returns one primer3-style dict per call."""
@@ -348,14 +410,27 @@ def design_primers_batch(seq_args_list, global_args=None, device=None):
         templates = [jobs[k].template for k in other_ix]
         masks = [jobs[k].mask for k in other_ix]
         list_off, recs = ctx.p3_candidates(s, templates, masks)
+        free, lefts, rmin = [], [], []
         for t, k in enumerate(other_ix):
             j = jobs[k]
-            L = recs[list_off[2 * t]:list_off[2 * t + 1]].copy()
-            R = recs[list_off[2 * t + 1]:list_off[2 * t + 2]].copy()
+            L = recs[list_off[2 * t]:list_off[2 * t + 1]]
+            R = recs[list_off[2 * t + 1]:list_off[2 * t + 2]]
             if j.left is not None:     # both primers given: libprimer3 evaluates that single pair
-                L = L[(L["start"] == j.left[0]) & (L["len"] == j.left[1])]
-                R = R[(R["start"] == j.right[0]) & (R["len"] == j.right[1])]
-            out[k] = _result_dict(_search_two_sided(ctx, s, L, R, j.target))
+                L = L[(L["start"] == j.left[0]) & (L["len"] == j.left[1])].copy()
+                R = R[(R["start"] == j.right[0]) & (R["len"] == j.right[1])].copy()
+                out[k] = _result_dict(_search_two_sided(ctx, s, L, R, j.target))
+            elif len(L) == 0 or len(R) == 0:
+                out[k] = _result_dict([])
+            else:
+                free.append(t)
+                lefts.append(L)
+                rmin.append(float(R["penalty"][0]))
+        if free:
+            targets = np.array([jobs[other_ix[t]].target for t in free], dtype=np.int32)
+            res = _search_two_sided_batch(ctx, s, [templates[t] for t in free], [masks[t] for t in free], targets,
+                                          lefts, rmin)
+            for t, rows_ in zip(free, res):
+                out[other_ix[t]] = _result_dict(rows_)
     return out
 
 

@@ -314,3 +314,37 @@ def test_picker_edge_cases(ctx, oracle):
     assert [res["PRIMER_LEFT_%d_SEQUENCE" % i] for i in range(len(ref))] == [e["left"]["seq"] for e in ref]
     assert [res["PRIMER_RIGHT_%d" % i] for i in range(len(ref))] == [(e["right"]["start"], e["right"]["len"]) for e in ref]
     p3b.resetP3Globals()
+
+
+@pytest.mark.gpu
+def test_two_sided_batch_matches_oracle(ctx, oracle):
+    # several templates in one call (the CAPS / HRM call shape: both primers picked around a target),
+    # including one whose first size range cannot fill the request and one with very few candidates
+    rng = np.random.default_rng(23)
+    g = {**KASP_GLOBALS, "PRIMER_NUM_RETURN": 9, "PRIMER_PRODUCT_SIZE_RANGE": [[60, 80], [50, 130]]}
+    p3b.resetP3Globals()
+    p3b.setP3Globals(g)
+    so = oracle_settings(g, 9)
+    cases = [(rand_template(rng, 190), (90, 5), [(0, 6)]), (rand_template(rng, 150, gc=0.5), (70, 2), []),
+             (rand_template(rng, 110), (50, 4), [(0, 20), (90, 20)]), (rand_template(rng, 160, gc=0.3), None, [])]
+    args = []
+    for t, target, excl in cases:
+        a = {"SEQUENCE_TEMPLATE": t}
+        if target:
+            a["SEQUENCE_TARGET"] = list(target)
+        if excl:
+            a["SEQUENCE_EXCLUDED_REGION"] = [list(x) for x in excl]
+        args.append(a)
+    got = p3b.design_primers_batch(args)
+    n = 0
+    for (t, target, excl), res in zip(cases, got):
+        ref = p3_oracle.design(oracle, so, t, excluded=excl, target=target)
+        assert res["PRIMER_PAIR_NUM_RETURNED"] == len(ref)
+        for i, e in enumerate(ref):
+            assert res["PRIMER_LEFT_%d" % i] == (e["left"]["start"], e["left"]["len"])
+            assert res["PRIMER_RIGHT_%d" % i] == (e["right"]["start"], e["right"]["len"])
+            assert res["PRIMER_PAIR_%d_PENALTY" % i] == e["pair_penalty"]
+            assert res["PRIMER_PAIR_%d_COMPL_END_TH" % i] == e["compl_end_th"]
+        n += len(ref)
+    assert n >= 18
+    p3b.resetP3Globals()
