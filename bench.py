@@ -317,7 +317,7 @@ def run_b200(args, rank, world, local_rank):
                     "relaxations_per_launch": relax_het, "flop_per_relaxation": FLOP_PER_RELAXATION,
                     "kernel_ms": het_ms, "share_of_step": het_ms / (dev_ms / args.steps),
                     # ncu --set full, 400k-pair launch of this kernel: dram__bytes_read.sum 12.916 MB +
-                    # dram__bytes_write.sum 0.007 MB (profiles/r1_v6_ncu_full_summary.txt) = 32.3 B per
+                    # dram__bytes_write.sum 0.007 MB (profiles/r1_v6_ncu_full_summary.txt, r1_v7_ncu_full_summary.txt) = 32.3 B per
                     # pair, i.e. the two 16-byte input records; scaled to this launch's pair count
                     "traffic": 32.31 * n,
                     "traffic_note": "DRAM bytes per launch scaled from the ncu capture of a 400k-pair launch "
