@@ -416,7 +416,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
 
 // Capacity tiers.  The first pass keeps the per-warp shared-memory workspace
 // small (random 18-30 nt pairs have ~144 finite cells, <0.02% exceed 256) so
-// that 24-32 warps are resident per SM; items that exceed a tier's capacity are
+// that 26-28 warps are resident per SM; items that exceed a tier's capacity are
 // queued for the next one (reporter-tailed KASP pairs, then low-complexity /
 // 60-mer inputs whose DP table is dense).  Counters: ctr[0] work1, ctr[1]
 // list1_n, ctr[2] work2, ctr[3] list2_n, ctr[4] work3, ctr[5] unused, ctr[7] relaxations.
