@@ -84,3 +84,52 @@ def gather_to_rank0(local, dist):
     if dist.get_rank() != 0:
         return None
     return {key: np.concatenate([b[key] for b in bucket]) for key in bucket[0]}
+
+
+# ---- marker sets (BASELINE config 5) -----------------------------------------------------------
+def slice_markers(data, start, stop):
+    """The markers [start, stop) of a kasp_pipeline marker set (same dict layout)."""
+    out = {}
+    for k in ("templates", "starts", "marker_idx", "ref_len"):
+        out[k] = data[k][start:stop]
+    out["alt"] = list(data["alt"][start:stop])
+    out["maps"] = {name: m[start:stop] for name, m in data["maps"].items()}
+    if data.get("mut_seg") is not None:
+        seg = np.asarray(data["mut_seg"], dtype=np.int64)
+        a0, a1 = int(seg[start]), int(seg[stop])
+        out["mut_seg"] = seg[start:stop + 1] - a0
+        for k in ("mut_pos", "mut_aaf", "mut_indel"):
+            out[k] = data[k][a0:a1]
+    else:
+        out["mut_seg"] = None
+    return out
+
+
+def merge_marker_results(parts):
+    """Concatenates per-shard results of kasp_pipeline.design_markers_arrays in shard order:
+    pair arrays are appended, per-marker segment offsets and selected-pair indices are shifted."""
+    out = {k: np.concatenate([p[k] for p in parts]) for k in ("f", "r", "a", "dir", "goodness", "qbits", "n_sel")}
+    seg, sel, off = [np.zeros(1, dtype=np.int64)], [], 0
+    for p in parts:
+        seg.append(p["seg"][1:] + off)
+        sel.append(np.where(p["sel"] >= 0, p["sel"] + off, -1))
+        off += int(p["seg"][-1])
+    out["seg"] = np.concatenate(seg)
+    out["sel"] = np.concatenate(sel)
+    return out
+
+
+def design_markers_sharded(data, rank, world, dist=None, **kw):
+    """One rank's share of a marker set under torchrun (contiguous, equally sized ranges: every
+    marker of the synthetic set costs about the same); rank 0 receives the merged result when
+    ``dist`` (an initialised torch.distributed, gloo or nccl) is given.  No data-path collective:
+    the only communication is the host-side gather of the results."""
+    from . import kasp_pipeline
+    n = len(data["starts"])
+    lo, hi = shard_bounds(n, rank, world)
+    local = kasp_pipeline.design_markers_arrays(slice_markers(data, lo, hi), **kw)
+    if dist is None:
+        return local
+    bucket = [None] * world if rank == 0 else None
+    dist.gather_object(local, bucket, dst=0)
+    return merge_marker_results(bucket) if rank == 0 else None

@@ -149,6 +149,62 @@ def test_two_rank_gloo_shard_and_gather():
     assert scores == [u * 2.5 for u in range(101)]
 
 
+def _set_kasp_design_globals():
+    from polyoligo_b200 import lib_primer3 as lp, primer3_bindings as p3b
+    p3b.resetP3Globals()
+    lp.PRIMER3_GLOBALS.clear()
+    lp.set_globals(PRIMER_OPT_SIZE=20, PRIMER_MIN_SIZE=18, PRIMER_MAX_SIZE=25, PRIMER_OPT_TM=60.0, PRIMER_MIN_TM=55.0,
+                   PRIMER_MAX_TM=65.0, PRIMER_MIN_GC=20.0, PRIMER_MAX_GC=80.0, PRIMER_MAX_POLY_X=100,
+                   PRIMER_PAIR_MAX_DIFF_TM=6.0, PRIMER_PRODUCT_SIZE_RANGE=[[90, 150], [100, 200]],
+                   PRIMER_NUM_RETURN=8)
+    lp.set_tm_delta(5.0)
+
+
+def _gloo_marker_worker(rank, world, port, q):
+    # the real config-5 pipeline per rank; the CPU oracle context stands in for the GPU
+    import sys
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from oracle.cpu_pipeline import CpuContext
+    from polyoligo_b200 import kasp_pipeline as kp
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _set_kasp_design_globals()
+    data = kp.synth_config5(5, seed=3, length=300)
+    merged = sharding.design_markers_sharded(data, rank, world, dist=dist, n_primers=3, ctx=CpuContext(nthreads=2))
+    if rank == 0:
+        q.put({k: v.tolist() if k not in ("f", "r", "a") else v.tobytes() for k, v in merged.items()})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_marker_design_matches_single_process():
+    import sys
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from oracle.cpu_pipeline import CpuContext
+    from polyoligo_b200 import kasp_pipeline as kp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_marker_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _set_kasp_design_globals()
+    data = kp.synth_config5(5, seed=3, length=300)
+    one = kp.design_markers_arrays(data, n_primers=3, ctx=CpuContext(nthreads=2))
+    assert len(one["f"]) > 5
+    for k, v in one.items():
+        assert got[k] == (v.tobytes() if k in ("f", "r", "a") else v.tolist()), k
+    # slicing keeps the mutation segments consistent
+    part = sharding.slice_markers(data, 2, 5)
+    assert len(part["alt"]) == 3 and part["mut_seg"][0] == 0 and part["mut_seg"][-1] == len(part["mut_pos"])
+
+
 def test_ambiguous_sequences_and_mutation_labels():
     # string half of PrimerPair.add_mutations (reference lib_primer3.py:166-199) on hand-checked cases
     import types
