@@ -194,6 +194,7 @@ def run_b200(args, rank, world, local_rank):
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = po.Context(local_rank)   # raises if the CUDA library is missing: no CPU fallback
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     n = args.pairs
 
     # ---- workload: pinned host records and device-resident copies ------------
@@ -326,7 +327,19 @@ def run_b200(args, rank, world, local_rank):
                     "hbm": {"achieved_gbs": hbm_bytes / (het_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                             "frac": hbm_bytes / (het_ms * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
-                    "note": "compute-bound max-plus style DP on CUDA cores; not an HBM or tensor-core kernel (SURVEY 8d)"}
+                    # the binding resource: warp-instruction issue.  Instructions per pair come from the
+                    # ncu capture (smsp__inst_executed.sum 27,438,502,994 for a 400k-pair launch,
+                    # profiles/r1_v7_ncu_full_summary.txt); peak = 4 schedulers x SMs x SM clock
+                    "issue_slots": {"warp_instructions_per_pair": 68596,
+                                    "achieved_ginst_s": 68596 * n / (het_ms * 1e-3) / 1e9,
+                                    "peak_ginst_s": 4 * sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
+                                    "frac": 68596 * n / (het_ms * 1e-3) /
+                                            (4 * sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                                    "source": "instruction count from the ncu capture of the same kernel, time from "
+                                              "this run's CUDA events"},
+                    "note": "compute-bound max-plus style DP on CUDA cores; not an HBM or tensor-core kernel (SURVEY 8d); "
+                            "the kernel is bound by instruction issue (issue_slots), the FP64 share of the "
+                            "instructions is small by construction"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
