@@ -51,7 +51,7 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
 #define PO_HAIRPIN_WARPS 14
 #endif
 template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS >= 12 ? 2 : 1))
+__global__ void __launch_bounds__(WARPS * 32, (WARPS >= 5 ? 2 : 1))
 k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po_thal_out* __restrict__ out,
        const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
        const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
@@ -419,7 +419,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
 // that 26-28 warps are resident per SM; items that exceed a tier's capacity are
 // queued for the next one (reporter-tailed KASP pairs, then low-complexity /
 // 60-mer inputs whose DP table is dense).  Counters: ctr[0] work1, ctr[1]
-// list1_n, ctr[2] work2, ctr[3] list2_n, ctr[4] work3, ctr[5] unused, ctr[7] relaxations.
+// list1_n, ctr[2] work2, ctr[3] list2_n, ctr[4] work3, ctr[5] list3_n, ctr[6] work4, ctr[7] relaxations.
 // d_out2 (dimer types only): ANY result to d_out and END1 result to d_out2 from ONE table fill
 // (libprimer3 asks for both on every oligo and pair; the fill is > 90 % of the work).
 template <bool COUNT>
@@ -430,7 +430,7 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
     int rc = ensure(ctx, ctx->overflow, 2 * sizeof(long long) * (size_t)n);
     if (rc) return rc;
     unsigned long long* ctr = ctx->d_ctr;
-    CK(cudaMemsetAsync(ctr, 0, 6 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctr, 0, 7 * sizeof(unsigned long long), st));
     const uint4* A = (const uint4*)d_a;
     const uint4* B = (const uint4*)d_b;
     po_thal_out* out = (po_thal_out*)d_out;
@@ -458,8 +458,11 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
     else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
     else rc = launch_thal<256, PO_DIMER_WARPS, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
     if (rc) return rc;
-    if ((rc = launch_thal<512, 8, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em, out2))) return rc;
-    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em, out2);
+    // reporter-tailed KASP pairs (<= 47 x 26 nt, ~230-400 finite cells) mostly land in the second tier
+    if ((rc = launch_thal<384, 9, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em, out2))) return rc;
+    // l1 is fully consumed by now: its storage takes the third tier's overflow (own counter)
+    if ((rc = launch_thal<768, 5, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em, out2))) return rc;
+    return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 6, l1, ctr + 5, l2, ctr + 3, rx, em, out2);
 }
 
 extern "C" int po_thal_batch_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int64_t n, void* d_out,
