@@ -348,3 +348,24 @@ def test_two_sided_batch_matches_oracle(ctx, oracle):
         n += len(ref)
     assert n >= 18
     p3b.resetP3Globals()
+
+
+@pytest.mark.gpu
+def test_long_template_lists_use_the_global_sort_path(ctx):
+    # > 4096 candidates per list: the per-list bitonic sort leaves shared memory for global scratch
+    rng = np.random.default_rng(77)
+    t = rand_template(rng, 5200, gc=0.5)
+    s = _gpu_settings(5)
+    list_off, recs = ctx.p3_candidates(s, [t, rand_template(rng, 300)])
+    assert list_off[1] - list_off[0] > 4096 and list_off[2] - list_off[1] > 4096
+    so = {**p3_oracle.DEFAULTS, **oracle_settings(KASP_GLOBALS, 5)}
+    seqs = _native.unpack(recs["seq"])
+    for strand, side in enumerate("LR"):
+        ref = p3_oracle.candidates(so, t, [0] * len(t), side)
+        lo, hi = list_off[strand], list_off[strand + 1]
+        assert hi - lo == len(ref)
+        got = recs[lo:hi]
+        assert [int(x) for x in got["start"]] == [r["start"] for r in ref]
+        assert [int(x) for x in got["len"]] == [r["len"] for r in ref]
+        assert [float(x) for x in got["penalty"]] == [r["penalty"] for r in ref]
+        assert seqs[lo:hi] == [r["seq"] for r in ref]
