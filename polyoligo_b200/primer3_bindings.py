@@ -320,7 +320,7 @@ def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_
     range only fills what the earlier ones left open."""
     n = len(templates)
     want_total = s.num_return
-    rows = [[] for _ in range(n)]
+    acc = [[] for _ in range(n)]      # per template: (fixed records, pair records) of finished device calls
     covered = [0] * n
     result = [None] * n
     M = 64
@@ -336,37 +336,48 @@ def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_
             covered[t] = hi
         if tasks:
             tasks = np.array(tasks, dtype=_native.P3_TASK_DTYPE)
+            owner = np.array(owner)
             fixed, pairs, n_pairs = ctx.p3_design_fixed(s, templates, tasks, masks, targets)
-            for k, t in enumerate(owner):
-                l = fixed[k]
-                for p in pairs[k, :n_pairs[k]]:
-                    r = p["other"]
-                    cm = (r["self_end_th"] + l["self_end_th"] + p["compl_end_th"]) * 1.1 + r["self_any_th"] + \
-                        l["self_any_th"] + p["compl_any_th"]
-                    key = (float(p["pair_penalty"]), float(cm), -int(l["start"]), int(r["start"]), int(l["len"]),
-                           int(r["len"]))
-                    rows[t].append((int(p["size_range"]), key, l.copy(), r.copy(), p))
+            k_idx, r_idx = np.nonzero(np.arange(s.num_return)[None, :] < n_pairs[:, None])
+            own = owner[k_idx]                      # non-decreasing: tasks were appended template by template
+            cuts = np.searchsorted(own, np.arange(n + 1))
+            for t in range(n):
+                if cuts[t + 1] > cuts[t]:
+                    sl = slice(cuts[t], cuts[t + 1])
+                    acc[t].append((fixed[k_idx[sl]], pairs[k_idx[sl], r_idx[sl]]))
         for t in range(n):
             if result[t] is not None:
                 continue
             all_left = covered[t] >= len(lefts[t])
             bound = np.inf if all_left else float(lefts[t]["penalty"][covered[t]]) + right_min_penalty[t]
+            if acc[t]:
+                l = np.concatenate([a[0] for a in acc[t]])
+                p = np.concatenate([a[1] for a in acc[t]])
+                r = p["other"]
+                cm = (r["self_end_th"] + l["self_end_th"] + p["compl_end_th"]) * 1.1 + r["self_any_th"] + \
+                    l["self_any_th"] + p["compl_any_th"]
+                # pair order inside a size range: penalty, compl_measure, left start descending, right
+                # start ascending, left length, right length (np.lexsort: last key is the primary one)
+                order = np.lexsort((r["len"], l["len"], r["start"], -l["start"].astype(np.int64), cm,
+                                    p["pair_penalty"], p["size_range"]))
+                l, p = l[order], p[order]
+            else:
+                l = np.zeros(0, dtype=_native.P3_OLIGO_DTYPE)
+                p = np.zeros(0, dtype=_native.P3_PAIR_DTYPE)
             chosen, complete = [], True
             for interval in range(s.n_size_ranges):
                 want = want_total - len(chosen)
                 if want <= 0:
                     break
-                cand = sorted((x for x in rows[t] if x[0] == interval), key=lambda x: x[1])
-                if all_left:
-                    chosen += cand[:want]
-                elif len(cand) >= want and cand[want - 1][1][0] < bound:
-                    chosen += cand[:want]
+                idx = np.flatnonzero(p["size_range"] == interval)
+                if all_left or (len(idx) >= want and p["pair_penalty"][idx[want - 1]] < bound):
+                    chosen += list(idx[:want])
                 else:
                     complete = False      # an uncovered left candidate could still enter this range
                     break
             if complete:
-                result[t] = [(l, r, p["pair_penalty"], p["compl_any_th"], p["compl_end_th"], p["product_size"])
-                             for _, _, l, r, p in chosen[:want_total]]
+                result[t] = [(l[i].copy(), p["other"][i].copy(), p["pair_penalty"][i], p["compl_any_th"][i],
+                              p["compl_end_th"][i], p["product_size"][i]) for i in chosen[:want_total]]
         M *= 4
     return result
 
@@ -422,6 +433,19 @@ def design_primers_batch(seq_args_list, global_args=None, device=None):
             elif len(L) == 0 or len(R) == 0:
                 out[k] = _result_dict([])
             else:
+                # left candidates that no right candidate can reach with an allowed product size (or
+                # that do not lie before the target) can never be in a pair: drop them up front
+                rs = np.sort(R["start"].astype(np.int64))
+                ls = L["start"].astype(np.int64)
+                lo_ = min(s.size_lo[:s.n_size_ranges]) if s.n_size_ranges else 0
+                hi_ = max(s.size_hi[:s.n_size_ranges]) if s.n_size_ranges else -1
+                reach = np.searchsorted(rs, ls + hi_ - 1, side="right") > np.searchsorted(rs, ls + lo_ - 1, side="left")
+                if j.target[1] > 0:
+                    reach &= (ls + L["len"] - 1 < j.target[0]) & (ls + hi_ - 1 >= j.target[0] + j.target[1])
+                L = L[reach]
+                if len(L) == 0:
+                    out[k] = _result_dict([])
+                    continue
                 free.append(t)
                 lefts.append(L)
                 rmin.append(float(R["penalty"][0]))
