@@ -65,6 +65,7 @@ __device__ __forceinline__ int dimer_build_runs(const Grp<G>& g, const SmemTable
     int carry = 0;
 #pragma unroll
     for (int sl = 0; sl < 32 / G; ++sl) {
+        if (sl * G >= ci - 1) break;  // no predecessor row that far up (warp-uniform: one row per batch)
         const int l1 = sl * G + g.lane, r = ci - 1 - l1;
         const bool have = (r >= 1) & (l1 <= max_loop);
         const int rr = have ? r : 1;
@@ -76,7 +77,7 @@ __device__ __forceinline__ int dimer_build_runs(const Grp<G>& g, const SmemTable
         const int first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
         const int incl = g.scan_incl(cnt) + carry;
         rt.end[l1] = (uint16_t)incl;
-        rt.first[l1] = (uint16_t)first;
+        rt.adj[l1] = (int16_t)(first - (incl - cnt));
         carry = g.shfl(incl, G - 1);
     }
     const bool cAT = (cb == 0) | (cb == 3);
@@ -103,11 +104,12 @@ __device__ __forceinline__ void dimer_scan(const Grp<G>& g, const TabAddr& A, co
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 bestV = make_double2(PO_INF, -1.0);
+    const bool half = c.ci - 1 <= 16;
     for (int t0 = 0; t0 < trip_total; t0 += G) {
         const int t = t0 + g.lane;
         bool act = t < total;
         int key;
-        const double2 v = dimer_loop_value<CAP>(A, ws, yc, c, run_lookup(rt, act ? t : 0), &key);
+        const double2 v = dimer_loop_value<CAP>(A, ws, yc, c, run_lookup(rt, act ? t : 0, half), &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
         if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
@@ -394,7 +396,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             const int t = t0 + lane;
             const bool act = t < total;
             int key;
-            const double2 v = dimer_loop_value<CAP>(A, ws, ws.ycell[0], c, run_lookup(ws.runs[0], act ? t : 0), &key);
+            const double2 v = dimer_loop_value<CAP>(A, ws, ws.ycell[0], c, run_lookup(ws.runs[0], act ? t : 0, i - 1 <= 16), &key);
             const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
             // traceback mode of the 1x1 branch reports its value only when T1 >= T2
             const bool ok = act & (key < myKey) & ((key != KEY_STAR) | (T1 >= Tcur));

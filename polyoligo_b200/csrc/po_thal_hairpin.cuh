@@ -152,7 +152,7 @@ __device__ __forceinline__ int hairpin_build_runs(const Grp<G>& g, const SmemTab
         const int first = ws.start[jc] + __popcll(cm >> min(max(hi_row, 0), 63));
         const int incl = g.scan_incl(cnt) + carry;
         rt.end[l2] = (uint16_t)incl;
-        rt.first[l2] = (uint16_t)first;
+        rt.adj[l2] = (int16_t)(first - (incl - cnt));
         carry = g.shfl(incl, G - 1);
     }
     const bool cAT = (bi == 0) | (bi == 3);
@@ -184,7 +184,7 @@ __device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, 
     for (int t0 = 0; t0 < trip_total; t0 += G) {
         const int t = t0 + g.lane;
         bool act = t < total;
-        const int kp = run_lookup(rt, act ? t : 0);
+        const int kp = run_lookup(rt, act ? t : 0, false);
         int key;
         double2 v = hairpin_loop_term<CAP>(A, ws, yc, c, kp, &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
@@ -621,7 +621,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             for (int t0 = 0; t0 < total; t0 += 32) {
                 const int t = t0 + lane;
                 const bool act = t < total;
-                const int kp = run_lookup(ws.runs[0], act ? t : 0);
+                const int kp = run_lookup(ws.runs[0], act ? t : 0, false);
                 int key;
                 double2 v = hairpin_loop_term<CAP>(A, ws, ws.ycell[0], c, kp, &key);
                 v = hp_fix(v.x, v.y);  // traceback == 1 form: every branch reports its value
