@@ -27,23 +27,17 @@ __device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const Dime
     // stack[s1[pi]][s1[ci]][s2[pj]][s2[cj]] = pb*64 + cb*16 + (3-pb)*4 + c2
     const LoopOps o = loop_ops(A, ycell, l1, l2, CODE_TQ(code), pb, pb * 60 + 12 + c.b1q);
     *key_out = o.key;
-    double H = (o.L.x + o.P.x) + o.C.x;
-    double S = ((o.L.y + o.P.y) + o.C.y) + o.asymS;
-    if (o.isB1 & ((H > 0) | (S > 0))) {
-        H = PO_INF;
-        S = -1.0;
-    }
-    H += pv.x;
-    S += pv.y;
-    if (!fin(H)) {
-        H = PO_INF;
-        S = -1.0;
-    }
-    if (!o.isB1 & (H > 0) & (S > 0)) {
-        H = PO_INF;
-        S = -1.0;
-    }
-    return make_double2(H, S);
+    // Upstream rejects in three places: a bulge of one whose own term is positive (before the
+    // earlier cell is added), a non-finite sum, and any other loop whose sum is positive in both
+    // components.  A rejected value is {inf, -1} and stays so through the later steps, so the three
+    // tests fold into one select.
+    const double H0 = (o.L.x + o.P.x) + o.C.x;
+    const double S0 = ((o.L.y + o.P.y) + o.C.y) + o.asymS;
+    const double H = H0 + pv.x, S = S0 + pv.y;
+    const bool own_positive = (H0 > 0.0) || (S0 > 0.0);
+    const bool sum_positive = (H > 0.0) && (S > 0.0);
+    const bool reject = !fin(H) || (o.isB1 ? own_positive : sum_positive);
+    return reject ? make_double2(PO_INF, -1.0) : make_double2(H, S);
 }
 
 // Candidate predecessors of cell (ci,cj): every finite (pi,pj) with pi < ci,
