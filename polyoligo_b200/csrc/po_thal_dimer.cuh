@@ -34,7 +34,8 @@ __device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const Dime
     const double H0 = (o.L.x + o.P.x) + o.C.x;
     const double S0 = ((o.L.y + o.P.y) + o.C.y) + o.asymS;
     const double H = H0 + pv.x, S = S0 + pv.y;
-    const bool own_positive = (H0 > 0.0) || (S0 > 0.0);
+    // x > 0 for a non-NaN double is "sign clear and not zero": one 64-bit integer compare
+    const bool own_positive = (__double_as_longlong(H0) > 0ll) | (__double_as_longlong(S0) > 0ll);
     const bool sum_positive = (H > 0.0) && (S > 0.0);
     const bool reject = !fin(H) || (o.isB1 ? own_positive : sum_positive);
     return reject ? make_double2(PO_INF, -1.0) : make_double2(H, S);

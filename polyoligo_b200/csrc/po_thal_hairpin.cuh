@@ -33,9 +33,11 @@ __device__ __forceinline__ double2 hairpin_loop_term(const TabAddr& A, const Hai
     // stack[s[i]][s[ii]][s[j]][s[jj]] = bi*64 + b*16 + bj*4 + (3-b)
     const LoopOps o = loop_ops(A, ycell, l1, l2, CODE_TQ(code), b, c.b1q + b * 15 + 3);
     *key_out = o.key;
-    // bulge of one: upstream sums bulge + stack only; otherwise closing side, then enclosed side
-    const double H = o.isB1 ? (o.L.x + o.P.x) + o.C.x : (o.L.x + o.C.x) + o.P.x;
-    const double S = (o.isB1 ? (o.L.y + o.P.y) + o.C.y : (o.L.y + o.C.y) + o.P.y) + o.asymS;
+    // closing side first, then the enclosed side.  For a bulge of one upstream sums bulge + stack
+    // only; there C is the {+0, +0} placeholder and L + (+0) is L exactly, so the same expression
+    // gives the same bits.
+    const double H = (o.L.x + o.C.x) + o.P.x;
+    const double S = ((o.L.y + o.C.y) + o.P.y) + o.asymS;
     return make_double2(H, S);
 }
 
