@@ -68,8 +68,10 @@ __device__ __forceinline__ int dimer_build_runs(const Grp<G>& g, const SmemTable
         int lo_col = max(1, cj - 1 - (max_loop - l1));        // l1 + l2 <= max_loop
         if (prune && !interior_ok && l1 > 0) lo_col = max(lo_col, cj - 1);
         const unsigned long long rm = ws.mask[3 - ws.s1[rr]];
-        const int cnt = have ? __popcll(rm & bit_range(lo_col - 1, hi_col - 1)) : 0;
-        const int first = ws.start[rr] + __popcll(rm & bit_range(0, lo_col - 2));
+        // columns lo_col .. hi_col (1-based) are bits lo_col-1 .. hi_col-1; lo_col >= 1, hi_col <= 60
+        const int below = popc_below(rm, lo_col - 1);
+        const int cnt = have ? max(popc_below(rm, max(hi_col, 0)) - below, 0) : 0;
+        const int first = ws.start[rr] + below;
         const int incl = g.scan_incl(cnt) + carry;
         rt.end[l1] = (uint16_t)incl;
         rt.adj[l1] = (int16_t)(first - (incl - cnt));

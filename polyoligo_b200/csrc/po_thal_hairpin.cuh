@@ -150,7 +150,8 @@ __device__ __forceinline__ int hairpin_build_runs(const Grp<G>& g, const SmemTab
         int hi_row = min(jc - 4, i + 1 + (max_loop - l2));        // l1 + l2 <= max_loop
         if (prune && !interior_ok && l2 > 0) hi_row = min(hi_row, i + 1);
         const unsigned long long cm = HP_COLMASK(ws, jc);
-        const int cnt = have ? __popcll(cm & bit_range(lo_row - 1, hi_row - 1)) : 0;
+        // rows lo_row .. hi_row (1-based) are bits lo_row-1 .. hi_row-1; lo_row >= 2
+        const int cnt = have ? max(popc_below(cm, min(max(hi_row, 0), 63)) - popc_below(cm, lo_row - 1), 0) : 0;
         const int first = ws.start[jc] + __popcll(cm >> min(max(hi_row, 0), 63));
         const int incl = g.scan_incl(cnt) + carry;
         rt.end[l2] = (uint16_t)incl;
