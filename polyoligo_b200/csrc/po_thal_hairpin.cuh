@@ -244,7 +244,7 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
         else if (v == 4) x = tb.tstack2[quad(bim, bi, bp2, bp)];        // Htstack(i-1, k+2)
         const double2 dv = ws.cell[kc];
         const double hk = ws.end5[0][kk], sk = ws.end5[1][kk];
-        const double T1p = po_div(hk + iH, sk + iS + RC);
+        const double T1p = ws.end5t[kk];   // == po_div(hk + iH, sk + iS + RC), kept when end5[kk] was set
         double H, S;
         const int pp = act ? p : 1, qq = act ? q : 1;
         const double aH = at_h(s[pp], s[qq]), aS = at_s(s[pp], s[qq]);
@@ -465,6 +465,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
     if (lane == 0) {
         ws.end5[1][0] = ws.end5[1][1] = -1.0;
         ws.end5[0][0] = ws.end5[0][1] = PO_INF;
+        ws.end5t[0] = ws.end5t[1] = po_div(PO_INF + iH, -1.0 + iS + RC);
     }
     __syncwarp();
     for (int i = 2; i <= len; ++i) {
@@ -475,7 +476,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
         const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
         if (any) {
             const double2 e = end5_all<CAP>(tb, ws, lane, i, iH, iS, RC);
-            const double T1 = po_div(hp + iH, sp + iS + RC);
+            const double T1 = ws.end5t[i - 1];
             const double Tv = po_div(e.x + iH, e.y + iS + RC);
             const double T2 = gw.shfl(Tv, 0), T3 = gw.shfl(Tv, 8), T4 = gw.shfl(Tv, 16), T5 = gw.shfl(Tv, 24);
             int mx;
@@ -494,9 +495,11 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             }
         }
         if (COUNT) cnt += (lane == 0) ? 4 : 0;
+        const double tn = po_div(hn + iH, sn + iS + RC);
         if (lane == 0) {
             ws.end5[0][i] = hn;
             ws.end5[1][i] = sn;
+            ws.end5t[i] = tn;
         }
         __syncwarp();
     }
