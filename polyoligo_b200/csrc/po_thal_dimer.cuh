@@ -235,7 +235,8 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                     S1 = pv.y + st.y;
                     H1 = pv.x + st.x;
                 }
-                const double T1 = have ? po_div(H1 + iH + sh.x, S1 + iS + RC + sh.y) : po_div(H1 + iH, S1 + iS + RC);
+                // without a stackable predecessor upstream divides {inf + iH} by {-1 + iS + RC} < 0: -inf
+                const double T1 = have ? po_div(H1 + iH + sh.x, S1 + iS + RC + sh.y) : -PO_INF;
                 if (S1 < PO_MIN_ENTROPY_CUTOFF) {
                     S1 = PO_MIN_ENTROPY;
                     H1 = 0.0;

@@ -356,6 +356,8 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
     __syncwarp();
 
     int cnt = 0;
+    // maxTM2's empty-structure quotient (0 + iH) / (MIN_ENTROPY + iS + RC): the same for every cell
+    const double T0_const = po_div(0.0 + iH, PO_MIN_ENTROPY + iS + RC);
     // ---- fillMatrix2 -----------------------------------------------------------
     for (int j = 5; j <= len; ++j) {
         const int cs = ws.start[j], ce = ws.start[j + 1];
@@ -366,7 +368,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const int k = act ? k0 + lane : ce - 1;
             const int i = CODE_I(ws.code[k]);
             double S0 = PO_MIN_ENTROPY, H0 = 0.0;
-            const double T0 = po_div(H0 + iH, S0 + iS + RC);
+            const double T0 = T0_const;
             const bool pfin = hp_finite<CAP>(ws, i + 1, j - 1);
             double2 pv = ws.cell[pfin ? hp_index<CAP>(ws, i + 1, j - 1) : 0];
             if (!pfin) pv = make_double2(PO_INF, -1.0);
