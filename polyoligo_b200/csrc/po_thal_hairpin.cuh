@@ -143,6 +143,7 @@ __device__ __forceinline__ int hairpin_build_runs(const Grp<G>& g, const SmemTab
     int carry = 0;
 #pragma unroll
     for (int sl = 0; sl < 32 / G; ++sl) {
+        if (sl * G > j - 6) break;  // columns j-1 .. 5 only: no run that far (warp-uniform: one column per batch)
         const int l2 = sl * G + g.lane, jj = j - 1 - l2;
         const bool have = (jj >= 5) & (l2 <= max_loop);
         const int jc = have ? jj : 5;
@@ -187,7 +188,7 @@ __device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, 
     for (int t0 = 0; t0 < trip_total; t0 += G) {
         const int t = t0 + g.lane;
         bool act = t < total;
-        const int kp = run_lookup(rt, act ? t : 0, false);
+        const int kp = run_lookup(rt, act ? t : 0, G < 32 && c.j - 6 < 16);
         int key;
         double2 v = hairpin_loop_term<CAP>(A, ws, yc, c, kp, &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
