@@ -318,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
                     "relaxations_per_launch": relax_het, "flop_per_relaxation": FLOP_PER_RELAXATION,
                     "kernel_ms": het_ms, "share_of_step": het_ms / (dev_ms / args.steps),
                     # ncu --set full, 400k-pair launch of this kernel: dram__bytes_read.sum 12.889 MB +
-                    # dram__bytes_write.sum 0.019 MB (profiles/r1_v9_ncu_full_summary.txt) = 32.3 B per
+                    # dram__bytes_write.sum 0.019 MB (profiles/r1_v10_ncu_full_summary.txt) = 32.3 B per
                     # pair, i.e. the two 16-byte input records; scaled to this launch's pair count
                     "traffic": 32.31 * n,
                     "traffic_note": "DRAM bytes per launch scaled from the ncu capture of a 400k-pair launch "
@@ -328,12 +328,12 @@ def run_b200(args, rank, world, local_rank):
                             "frac": hbm_bytes / (het_ms * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650"},
                     # the binding resource: warp-instruction issue.  Instructions per pair come from the
-                    # ncu capture (smsp__inst_executed.sum 24,975,732,705 for a 400k-pair launch,
-                    # profiles/r1_v9_ncu_full_summary.txt); peak = 4 schedulers x SMs x SM clock
-                    "issue_slots": {"warp_instructions_per_pair": 62440,
-                                    "achieved_ginst_s": 62440 * n / (het_ms * 1e-3) / 1e9,
+                    # ncu capture (smsp__inst_executed.sum 23,692,710,893 for a 400k-pair launch,
+                    # profiles/r1_v10_ncu_full_summary.txt); peak = 4 schedulers x SMs x SM clock
+                    "issue_slots": {"warp_instructions_per_pair": 59230,
+                                    "achieved_ginst_s": 59230 * n / (het_ms * 1e-3) / 1e9,
                                     "peak_ginst_s": 4 * sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e9,
-                                    "frac": 62440 * n / (het_ms * 1e-3) /
+                                    "frac": 59230 * n / (het_ms * 1e-3) /
                                             (4 * sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6),
                                     "source": "instruction count from the ncu capture of the same kernel, time from "
                                               "this run's CUDA events"},

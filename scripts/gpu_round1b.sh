@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
     python bench.py $SMALL > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?"
 python bench.py $SMALL > gpurun_out/plain_small2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_thal -s 28 -c 5 -f -o gpurun_out/prof_r1_v9 \
+ncu --set full --clock-control none --import-source on -k regex:k_thal -s 28 -c 5 -f -o gpurun_out/prof_r1_v10 \
     python bench.py $SMALL > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out | tail -12
