@@ -13,7 +13,6 @@ There is no CPU fallback: without the CUDA library or a GPU the first call raise
 import os
 import threading
 
-import numpy as np
 
 from . import _native
 
