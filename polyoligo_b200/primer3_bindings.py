@@ -310,24 +310,32 @@ def _search_two_sided(ctx, s, L, R, target):
     return accepted
 
 
-def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_penalty):
+def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_penalty, per_left=None):
     """Both primers picked, for many templates at once, on top of the device's fixed-primer search:
     every one of the best M left candidates of a template becomes a 'left primer given' task (one
-    device call for all templates), and the per-left answers are merged.  Pairs of the left
-    candidates not yet covered have a penalty of at least L[M].penalty + R[0].penalty, so the merge
-    is final once the wanted number of pairs lies strictly below that bound (or every left
-    candidate has been covered); otherwise M grows.  Size ranges are honoured in order: a later
-    range only fills what the earlier ones left open."""
+    device call for all templates), and the per-left answers are merged.  The merge is final when
+    the wanted number of pairs lies strictly below every bound on what has not been seen:
+      * left candidates not yet covered: pair penalty >= L[M].penalty + R[0].penalty (else M grows);
+      * with ``per_left`` < num_return each task returns only its best ``per_left`` pairs; a task
+        that filled its quota may hold more pairs, all at or above the penalty of its last one.
+    A template that cannot be settled under the per-left quota is returned as None (the caller runs
+    it again without the quota).  Size ranges are honoured in order: a later range only fills what
+    the earlier ones left open."""
     n = len(templates)
     want_total = s.num_return
+    quota = want_total if per_left is None else min(per_left, want_total)
+    dev = _native.P3Settings.from_buffer_copy(s)
+    dev.num_return = quota
     acc = [[] for _ in range(n)]      # per template: (fixed records, pair records) of finished device calls
+    full = [[] for _ in range(n)]     # per template: (size range, penalty) of the last pair of every full task
     covered = [0] * n
     result = [None] * n
+    given_up = [False] * n
     M = 64
-    while any(r is None for r in result):
+    while any(result[t] is None and not given_up[t] for t in range(n)):
         tasks, owner = [], []
         for t in range(n):
-            if result[t] is not None:
+            if result[t] is not None or given_up[t]:
                 continue
             hi = min(M, len(lefts[t]))
             for li in range(covered[t], hi):
@@ -337,16 +345,20 @@ def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_
         if tasks:
             tasks = np.array(tasks, dtype=_native.P3_TASK_DTYPE)
             owner = np.array(owner)
-            fixed, pairs, n_pairs = ctx.p3_design_fixed(s, templates, tasks, masks, targets)
-            k_idx, r_idx = np.nonzero(np.arange(s.num_return)[None, :] < n_pairs[:, None])
+            fixed, pairs, n_pairs = ctx.p3_design_fixed(dev, templates, tasks, masks, targets)
+            k_idx, r_idx = np.nonzero(np.arange(quota)[None, :] < n_pairs[:, None])
             own = owner[k_idx]                      # non-decreasing: tasks were appended template by template
             cuts = np.searchsorted(own, np.arange(n + 1))
             for t in range(n):
                 if cuts[t + 1] > cuts[t]:
                     sl = slice(cuts[t], cuts[t + 1])
                     acc[t].append((fixed[k_idx[sl]], pairs[k_idx[sl], r_idx[sl]]))
+            if quota < want_total:
+                for k in np.flatnonzero(n_pairs == quota):
+                    last = pairs[k, quota - 1]
+                    full[owner[k]].append((int(last["size_range"]), float(last["pair_penalty"])))
         for t in range(n):
-            if result[t] is not None:
+            if result[t] is not None or given_up[t]:
                 continue
             all_left = covered[t] >= len(lefts[t])
             bound = np.inf if all_left else float(lefts[t]["penalty"][covered[t]]) + right_min_penalty[t]
@@ -370,10 +382,17 @@ def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_
                 if want <= 0:
                     break
                 idx = np.flatnonzero(p["size_range"] == interval)
-                if all_left or (len(idx) >= want and p["pair_penalty"][idx[want - 1]] < bound):
+                # tasks that filled their quota in an EARLIER range never showed this range at all
+                blocked = any(k < interval for k, _ in full[t])
+                quota_bound = min([q for k, q in full[t] if k == interval], default=np.inf)
+                if all_left and not blocked and quota_bound == np.inf:
+                    chosen += list(idx[:want])                        # everything there is
+                elif not blocked and len(idx) >= want and p["pair_penalty"][idx[want - 1]] < min(bound, quota_bound):
                     chosen += list(idx[:want])
                 else:
-                    complete = False      # an uncovered left candidate could still enter this range
+                    complete = False
+                    if blocked or (len(idx) >= want and p["pair_penalty"][idx[want - 1]] >= quota_bound) or all_left:
+                        given_up[t] = True            # more left candidates cannot settle it: the quota is in the way
                     break
             if complete:
                 result[t] = [(l[i].copy(), p["other"][i].copy(), p["pair_penalty"][i], p["compl_any_th"][i],
@@ -451,8 +470,16 @@ def design_primers_batch(seq_args_list, global_args=None, device=None):
                 rmin.append(float(R["penalty"][0]))
         if free:
             targets = np.array([jobs[other_ix[t]].target for t in free], dtype=np.int32)
-            res = _search_two_sided_batch(ctx, s, [templates[t] for t in free], [masks[t] for t in free], targets,
-                                          lefts, rmin)
+            sub_t, sub_m = [templates[t] for t in free], [masks[t] for t in free]
+            # first with a small per-left quota (the best pairs of a template rarely share a left primer
+            # more than a few times), then without it for the templates the quota could not settle
+            res = _search_two_sided_batch(ctx, s, sub_t, sub_m, targets, lefts, rmin, per_left=16)
+            redo = [i for i, r_ in enumerate(res) if r_ is None]
+            if redo:
+                again = _search_two_sided_batch(ctx, s, [sub_t[i] for i in redo], [sub_m[i] for i in redo],
+                                                targets[redo], [lefts[i] for i in redo], [rmin[i] for i in redo])
+                for i, r_ in zip(redo, again):
+                    res[i] = r_
             for t, rows_ in zip(free, res):
                 out[other_ix[t]] = _result_dict(rows_)
     return out

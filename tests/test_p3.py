@@ -369,3 +369,29 @@ def test_long_template_lists_use_the_global_sort_path(ctx):
         assert [int(x) for x in got["len"]] == [r["len"] for r in ref]
         assert [float(x) for x in got["penalty"]] == [r["penalty"] for r in ref]
         assert seqs[lo:hi] == [r["seq"] for r in ref]
+
+
+@pytest.mark.gpu
+def test_two_sided_per_left_quota_is_exact(ctx, oracle):
+    # more pairs wanted than the per-left quota of the first pass (16): the quota bounds must either
+    # prove the merge final or send the template to the unrestricted second pass
+    rng = np.random.default_rng(101)
+    g = {**KASP_GLOBALS, "PRIMER_NUM_RETURN": 40, "PRIMER_PRODUCT_SIZE_RANGE": [[60, 90], [50, 160]]}
+    p3b.resetP3Globals()
+    p3b.setP3Globals(g)
+    so = oracle_settings(g, 40)
+    cases = [(rand_template(rng, 300), None), (rand_template(rng, 260, gc=0.5), (125, 8)),
+             (rand_template(rng, 140), None)]
+    args = [{"SEQUENCE_TEMPLATE": t, **({"SEQUENCE_TARGET": list(tg)} if tg else {})} for t, tg in cases]
+    got = p3b.design_primers_batch(args)
+    n = 0
+    for (t, tg), res in zip(cases, got):
+        ref = p3_oracle.design(oracle, so, t, target=tg)
+        assert res["PRIMER_PAIR_NUM_RETURNED"] == len(ref)
+        for i, e in enumerate(ref):
+            assert res["PRIMER_LEFT_%d" % i] == (e["left"]["start"], e["left"]["len"]), i
+            assert res["PRIMER_RIGHT_%d" % i] == (e["right"]["start"], e["right"]["len"]), i
+            assert res["PRIMER_PAIR_%d_PENALTY" % i] == e["pair_penalty"]
+        n += len(ref)
+    assert n >= 60
+    p3b.resetP3Globals()
