@@ -326,7 +326,9 @@ def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_
     quota = want_total if per_left is None else min(per_left, want_total)
     dev = _native.P3Settings.from_buffer_copy(s)
     dev.num_return = quota
-    acc = [[] for _ in range(n)]      # per template: (fixed records, pair records) of finished device calls
+    calls = []                        # (fixed, pairs) of every device call: rows are gathered from here at the end
+    acc = [[] for _ in range(n)]      # per template: (call index, row slice) into that call's key arrays
+    keys = []                         # per call: dict of flat per-row key arrays (task index K, rank R, sort keys)
     full = [[] for _ in range(n)]     # per template: (size range, penalty) of the last pair of every full task
     covered = [0] * n
     result = [None] * n
@@ -346,13 +348,20 @@ def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_
             tasks = np.array(tasks, dtype=_native.P3_TASK_DTYPE)
             owner = np.array(owner)
             fixed, pairs, n_pairs = ctx.p3_design_fixed(dev, templates, tasks, masks, targets)
-            k_idx, r_idx = np.nonzero(np.arange(quota)[None, :] < n_pairs[:, None])
-            own = owner[k_idx]                      # non-decreasing: tasks were appended template by template
-            cuts = np.searchsorted(own, np.arange(n + 1))
+            K, R = np.nonzero(np.arange(quota)[None, :] < n_pairs[:, None])
+            oth = pairs["other"]
+            # only the scalar sort keys are gathered per row; whole records only for the chosen rows
+            kd = {"K": K, "R": R, "range": pairs["size_range"][K, R], "pq": pairs["pair_penalty"][K, R],
+                  "cm": (oth["self_end_th"][K, R] + fixed["self_end_th"][K] + pairs["compl_end_th"][K, R]) * 1.1 +
+                        oth["self_any_th"][K, R] + fixed["self_any_th"][K] + pairs["compl_any_th"][K, R],
+                  "nls": -fixed["start"][K].astype(np.int64), "rs": oth["start"][K, R],
+                  "ll": fixed["len"][K], "rl": oth["len"][K, R]}
+            calls.append((fixed, pairs))
+            keys.append(kd)
+            cuts = np.searchsorted(owner[K], np.arange(n + 1))      # owner[K] is non-decreasing
             for t in range(n):
                 if cuts[t + 1] > cuts[t]:
-                    sl = slice(cuts[t], cuts[t + 1])
-                    acc[t].append((fixed[k_idx[sl]], pairs[k_idx[sl], r_idx[sl]]))
+                    acc[t].append((len(calls) - 1, slice(cuts[t], cuts[t + 1])))
             if quota < want_total:
                 for k in np.flatnonzero(n_pairs == quota):
                     last = pairs[k, quota - 1]
@@ -362,41 +371,42 @@ def _search_two_sided_batch(ctx, s, templates, masks, targets, lefts, right_min_
                 continue
             all_left = covered[t] >= len(lefts[t])
             bound = np.inf if all_left else float(lefts[t]["penalty"][covered[t]]) + right_min_penalty[t]
-            if acc[t]:
-                l = np.concatenate([a[0] for a in acc[t]])
-                p = np.concatenate([a[1] for a in acc[t]])
-                r = p["other"]
-                cm = (r["self_end_th"] + l["self_end_th"] + p["compl_end_th"]) * 1.1 + r["self_any_th"] + \
-                    l["self_any_th"] + p["compl_any_th"]
-                # pair order inside a size range: penalty, compl_measure, left start descending, right
-                # start ascending, left length, right length (np.lexsort: last key is the primary one)
-                order = np.lexsort((r["len"], l["len"], r["start"], -l["start"].astype(np.int64), cm,
-                                    p["pair_penalty"], p["size_range"]))
-                l, p = l[order], p[order]
-            else:
-                l = np.zeros(0, dtype=_native.P3_OLIGO_DTYPE)
-                p = np.zeros(0, dtype=_native.P3_PAIR_DTYPE)
+            col = {f: (np.concatenate([keys[c][f][sl] for c, sl in acc[t]]) if acc[t] else np.zeros(0))
+                   for f in ("range", "pq", "cm", "nls", "rs", "ll", "rl")}
+            src = np.concatenate([np.full(sl.stop - sl.start, c) for c, sl in acc[t]]) if acc[t] else np.zeros(0, int)
+            row = np.concatenate([np.arange(sl.start, sl.stop) for c, sl in acc[t]]) if acc[t] else np.zeros(0, int)
+            # pair order inside a size range: penalty, compl_measure, left start descending, right start
+            # ascending, left length, right length (np.lexsort: the last key is the primary one)
+            order = np.lexsort((col["rl"], col["ll"], col["rs"], col["nls"], col["cm"], col["pq"], col["range"]))
+            rng_sorted, pq_sorted = col["range"][order], col["pq"][order]
             chosen, complete = [], True
             for interval in range(s.n_size_ranges):
                 want = want_total - len(chosen)
                 if want <= 0:
                     break
-                idx = np.flatnonzero(p["size_range"] == interval)
+                idx = np.flatnonzero(rng_sorted == interval)
                 # tasks that filled their quota in an EARLIER range never showed this range at all
                 blocked = any(k < interval for k, _ in full[t])
                 quota_bound = min([q for k, q in full[t] if k == interval], default=np.inf)
                 if all_left and not blocked and quota_bound == np.inf:
                     chosen += list(idx[:want])                        # everything there is
-                elif not blocked and len(idx) >= want and p["pair_penalty"][idx[want - 1]] < min(bound, quota_bound):
+                elif not blocked and len(idx) >= want and pq_sorted[idx[want - 1]] < min(bound, quota_bound):
                     chosen += list(idx[:want])
                 else:
                     complete = False
-                    if blocked or (len(idx) >= want and p["pair_penalty"][idx[want - 1]] >= quota_bound) or all_left:
+                    if blocked or (len(idx) >= want and pq_sorted[idx[want - 1]] >= quota_bound) or all_left:
                         given_up[t] = True            # more left candidates cannot settle it: the quota is in the way
                     break
             if complete:
-                result[t] = [(l[i].copy(), p["other"][i].copy(), p["pair_penalty"][i], p["compl_any_th"][i],
-                              p["compl_end_th"][i], p["product_size"][i]) for i in chosen[:want_total]]
+                rows_ = []
+                for i in chosen[:want_total]:
+                    c, rr = int(src[order[i]]), int(row[order[i]])
+                    fx, pr = calls[c]
+                    k, r = int(keys[c]["K"][rr]), int(keys[c]["R"][rr])
+                    p = pr[k, r]
+                    rows_.append((fx[k].copy(), p["other"].copy(), p["pair_penalty"], p["compl_any_th"],
+                                  p["compl_end_th"], p["product_size"]))
+                result[t] = rows_
         M *= 4
     return result
 
