@@ -195,3 +195,34 @@ def test_array_pipeline_matches_cpu_oracle_pipeline():
     for k in ("f", "r", "a"):
         assert gpu[k].tobytes() == cpu[k].tobytes(), k
     p3b.resetP3Globals()
+
+
+@pytest.mark.gpu
+def test_pcr_design_primers_end_to_end_with_the_real_picker():
+    # no canned answers: picker + validity + max_unique through the public mirror (properties only)
+    rng = np.random.default_rng(4)
+    seq = "".join(np.array(list("ACGT"))[rng.integers(0, 4, 400)])
+    lp.PRIMER3_GLOBALS.clear()
+    p3b.resetP3Globals()
+    lp.set_globals(PRIMER_OPT_SIZE=20, PRIMER_MIN_SIZE=18, PRIMER_MAX_SIZE=25, PRIMER_OPT_TM=60.0, PRIMER_MIN_TM=55.0,
+                   PRIMER_MAX_TM=65.0, PRIMER_MIN_GC=20.0, PRIMER_MAX_GC=80.0, PRIMER_MAX_POLY_X=100,
+                   PRIMER_PAIR_MAX_DIFF_TM=6.0, PRIMER_PRODUCT_SIZE_RANGE=[[80, 200]], PRIMER_NUM_RETURN=40,
+                   PRIMER_SALT_DIVALENT=0.0, PRIMER_DNTP_CONC=0.0)
+    lp.set_tm_delta(5.0)
+    roi = types.SimpleNamespace(seq=seq, chrom="chrQ", left_roi=types.SimpleNamespace(start=7000))
+    repo = pcr.design_primers([], roi, sequence_target=[190, 10], sequence_excluded_region=[[0, 10]], n_primers=6,
+                              max_unique=2)
+    assert 0 < len(repo) <= 6
+    used = {}
+    for pp in repo:
+        f, r = pp.primers["F"], pp.primers["R"]
+        assert seq[f.start - 7000:f.stop - 7000 + 1] == f.sequence
+        assert p3b._revcomp(seq[r.start - 7000:r.stop - 7000 + 1]) == r.sequence
+        assert f.stop - 7000 < 190 and r.start - 7000 >= 200 and f.start - 7000 >= 10
+        assert 80 <= pp.product_size <= 200 and pp.product_size == r.stop - f.start + 1
+        assert 55.0 <= f.tm <= 65.0 and 55.0 <= r.tm <= 65.0 and pp.chrom == "chrQ"
+        for p in (f, r):
+            used[p.sequence] = used.get(p.sequence, 0) + 1
+    assert max(used.values()) <= 2
+    assert [pp.penalty for pp in repo] == sorted(pp.penalty for pp in repo)
+    p3b.resetP3Globals()
