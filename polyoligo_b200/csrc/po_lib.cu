@@ -213,7 +213,7 @@ struct po_ctx {
     // grow-only device scratch
     DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow;
     DevBuf scratch[12];
-    DevBuf p3[26];  // primer picking (po_p3.cuh)
+    DevBuf p3[28];  // primer picking (po_p3.cuh)
     unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
     // pinned staging for the host entry points
     DevBuf h_in, h_out;

@@ -85,11 +85,17 @@ template <bool FILL>
 __global__ void k_p3_enum(const char* __restrict__ tmpl, const uint8_t* __restrict__ mask,
                           const long long* __restrict__ set_off, long long n_sets, const po_p3_settings S,
                           const PoConsts K, unsigned long long* __restrict__ counts,
-                          const long long* __restrict__ list_off, po_p3_oligo* __restrict__ pool) {
+                          const long long* __restrict__ list_off, po_p3_oligo* __restrict__ pool,
+                          unsigned long long* __restrict__ vmask) {
     const long long total = set_off[n_sets];
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= total) return;
     const int strand = blockIdx.y;
+    // the count pass records which lengths were accepted (bit L - min_size); the fill pass only
+    // re-evaluates those
+    unsigned long long accepted = 0ull;
+    const unsigned long long todo = FILL ? vmask[strand * total + g] : ~0ull;
+    if (FILL && todo == 0ull) return;
     const long long set = p3_find_set(set_off, n_sets, g);
     const long long off = set_off[set];
     const int n = (int)(set_off[set + 1] - off), p = (int)(g - off);
@@ -104,12 +110,14 @@ __global__ void k_p3_enum(const char* __restrict__ tmpl, const uint8_t* __restri
         w[(L - 1) >> 4] |= (uint32_t)b << (2 * ((L - 1) & 15));
         gc += (b == 1 || b == 2);
         if (L < S.min_size) continue;
+        if (FILL && !((todo >> (L - S.min_size)) & 1ull)) continue;
         uint4 o = make_uint4(w[0], w[1], w[2], (w[3] & 0x00ffffffu) | ((uint32_t)L << 24));
         double gcp;
         const double tm = oligo_tm(o, K, &gcp);
         if (gcp < S.min_gc || gcp > S.max_gc) continue;
         if (tm < S.min_tm || tm > S.max_tm) continue;
         if (!p3_sequence_rules(S, o, L)) continue;
+        accepted |= 1ull << (L - S.min_size);
         const unsigned long long slot = atomicAdd(&counts[2 * set + strand], 1ull);
         if (FILL) {
             po_p3_oligo r;
@@ -125,6 +133,7 @@ __global__ void k_p3_enum(const char* __restrict__ tmpl, const uint8_t* __restri
             pool[list_off[2 * set + strand] + (long long)slot] = r;
         }
     }
+    if (!FILL) vmask[strand * total + g] = accepted;
 }
 
 // ---------------------------------------------------------------------------
@@ -605,6 +614,7 @@ static int p3_build_lists(po_ctx* ctx, const po_p3_settings* s, const PoConsts& 
     if ((rc = ensure(ctx, sb[5], (size_t)(total_bases > 0 ? total_bases : 1)))) return rc;
     if ((rc = ensure(ctx, sb[6], 8 * (nl + 1)))) return rc;
     if ((rc = ensure(ctx, sb[7], 8 * (nl + 1)))) return rc;
+    if ((rc = ensure(ctx, sb[26], 16 * (size_t)(total_bases > 0 ? total_bases : 1)))) return rc;  // accepted-length masks
     CK(cudaMemcpyAsync(sb[2].p, set_off, 8 * (size_t)(n_sets + 1), cudaMemcpyHostToDevice, st));
     if (total_bases > 0) {
         CK(cudaMemcpyAsync(sb[4].p, tmpl, (size_t)total_bases, cudaMemcpyHostToDevice, st));
@@ -619,7 +629,7 @@ static int p3_build_lists(po_ctx* ctx, const po_p3_settings* s, const PoConsts& 
     const dim3 grid((unsigned)((total_bases + threads - 1) / threads), 2);
     CK(cudaMemsetAsync(d_counts, 0, 8 * nl, st));
     k_p3_enum<false><<<grid, threads, 0, st>>>((const char*)sb[4].p, d_mask, (const long long*)sb[2].p, n_sets, *s, K,
-                                               d_counts, nullptr, nullptr);
+                                               d_counts, nullptr, nullptr, (unsigned long long*)sb[26].p);
     ctx->launches++;
     CK(cudaGetLastError());
     std::vector<unsigned long long> counts(nl);
@@ -641,7 +651,8 @@ static int p3_build_lists(po_ctx* ctx, const po_p3_settings* s, const PoConsts& 
     CK(cudaMemcpyAsync(sb[7].p, L->scratch_off.data(), 8 * (nl + 1), cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(d_counts, 0, 8 * nl, st));
     k_p3_enum<true><<<grid, threads, 0, st>>>((const char*)sb[4].p, d_mask, (const long long*)sb[2].p, n_sets, *s, K,
-                                              d_counts, (const long long*)sb[3].p, (po_p3_oligo*)sb[0].p);
+                                              d_counts, (const long long*)sb[3].p, (po_p3_oligo*)sb[0].p,
+                                              (unsigned long long*)sb[26].p);
     ctx->launches++;
     CK(cudaGetLastError());
     const size_t smem = 2 * P3_SORT_SMEM_ELEMS * sizeof(unsigned long long);
