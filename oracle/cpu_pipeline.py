@@ -132,7 +132,14 @@ class CpuContext:
             tmpl = blob[off[k]:off[k + 1]].tobytes().decode("ascii")
             mask = [0] * len(tmpl) if m is None else list(m[off[k]:off[k + 1]])
             side = "L" if tk["side"] == 1 else "R"
-            f = p3_oracle.cheap_record(s, tmpl, mask, side, int(tk["start"]), int(tk["len"]))
+            # designPrimers locates the given primer by string search: first occurrence
+            # (reference lib_primer3.py:479 passes the sequence only)
+            st, ln = int(tk["start"]), int(tk["len"])
+            lo = st if side == "L" else st - ln + 1
+            if 0 <= lo and lo + ln <= len(tmpl):
+                first = tmpl.upper().find(tmpl[lo:lo + ln].upper())
+                st = first if side == "L" else first + ln - 1
+            f = p3_oracle.cheap_record(s, tmpl, mask, side, st, ln)
             if f is None:
                 continue
             p3_oracle.add_self(self.orc, s, [f], self.nthreads)

@@ -21,10 +21,13 @@ _COMP = str.maketrans("ACGT", "TGCA")
 
 
 def tm_nn(seq, dnac1=25, dnac2=25, Na=50, K=0, Tris=0):
+    # MeltingTemp._check(seq, "Tm_NN"): upper-case, back-transcribe, then DROP every base that is
+    # not in ("A", "C", "G", "T", "I") -- ambiguous / N bases are removed, nothing is raised.
     seq = "".join(seq.split()).upper().replace("U", "T")
-    if not seq or any(b not in "ACGT" for b in seq):
-        raise ValueError("Base not allowed for Tm_NN")
-    c_seq = seq.translate(_COMP)
+    seq = "".join(b for b in seq if b in "ACGTI")
+    if not seq:
+        raise ValueError("Base not allowed for Tm_NN")     # Biopython: IndexError on seq[0]
+    c_seq = seq.translate(_COMP)                            # I stays I
     nn = DNA_NN3
     delta_h = 0
     delta_s = 0
@@ -52,9 +55,11 @@ def tm_nn(seq, dnac1=25, dnac2=25, Na=50, K=0, Tris=0):
         if neighbors in nn:
             delta_h += nn[neighbors][0]
             delta_s += nn[neighbors][1]
-        else:
+        elif neighbors[::-1] in nn:
             delta_h += nn[neighbors[::-1]][0]
             delta_s += nn[neighbors[::-1]][1]
+        # else: strict=False -> _key_error only warns (a neighbour pair with an inosine against
+        # an inosine is in none of the tables) and the pair contributes nothing
     k = (dnac1 - (dnac2 / 2.0)) * 1e-9
     R = 1.987
     mon = (Na + K + Tris / 2.0) * 1e-3

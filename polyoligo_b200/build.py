@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpolyoligo_b200.so")
 SOURCES = ["po_lib.cu", "po_tables.cpp"]
-HEADERS = ["po_common.h", "po_thal.cuh", "po_thal_dimer.cuh", "po_thal_hairpin.cuh", "default_params.inc",
-           os.path.join("..", "..", "include", "polyoligo_b200.h")]
+PUBLIC_HEADER = os.path.join(HERE, "..", "include", "polyoligo_b200.h")
+SOURCE_SUFFIXES = (".cu", ".cuh", ".h", ".inc", ".cpp")
 
 
 def nvcc():
@@ -24,11 +24,28 @@ def nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def source_files():
+    """Every file the library is compiled from: all of csrc/ plus the public header."""
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(SOURCE_SUFFIXES)]
+    return files + [PUBLIC_HEADER]
+
+
+def source_hash():
+    """sha1 over the library's sources (names + contents); stamps profiles/current.json."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in source_files():
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(f) > t for f in source_files())
 
 
 def build(force=False, verbose=False, out=None, defines=()):

@@ -233,14 +233,36 @@ __global__ void k_p3_fixed_init(const char* __restrict__ tmpl, const uint8_t* __
     const int n = (int)(set_off[tk.set + 1] - off);
     po_p3_oligo r;
     memset(&r, 0, sizeof(r));
-    r.start = tk.start;
+    // libprimer3 locates a given primer by a case-insensitive string search (the right primer's
+    // reverse complement), i.e. at the FIRST occurrence of its sequence in the template
+    // (reference lib_primer3.py:479 hands designPrimers the sequence, not a position): a task that
+    // names a later copy of a repeated sequence is moved to the first one.
+    int start = tk.start;
+    {
+        const int lo = tk.side == 1 ? tk.start : tk.start - tk.len + 1;
+        if ((tk.side == 1 || tk.side == 2) && tk.len > 0 && lo > 0 && lo + tk.len <= n) {
+            for (int p = 0; p < lo; ++p) {
+                bool same = true;
+                for (int k = 0; k < tk.len; ++k)
+                    if ((tmpl[off + p + k] & 0xDF) != (tmpl[off + lo + k] & 0xDF)) {
+                        same = false;
+                        break;
+                    }
+                if (same) {
+                    start = tk.side == 1 ? p : p + tk.len - 1;
+                    break;
+                }
+            }
+        }
+    }
+    r.start = start;
     r.len = tk.len;
     r.set = tk.set;
     r.self_any_th = r.self_end_th = r.hairpin_th = CUDART_NAN;
     bool ok = (tk.side == 1 || tk.side == 2) && tk.len >= S.min_size && tk.len <= S.max_size && tk.len <= PO_MAX_OLIGO_LEN;
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     for (int k = 0; k < tk.len && ok; ++k) {
-        const int q = tk.side == 1 ? tk.start + k : tk.start - k;
+        const int q = tk.side == 1 ? start + k : start - k;
         if (q < 0 || q >= n) {
             ok = false;
             break;

@@ -271,12 +271,18 @@ struct TmNNConsts {
 __constant__ double c_nn3_h[16] = {-7.9, -8.4, -7.8, -7.2, -8.5, -8.0, -10.6, -7.8, -8.2, -9.8, -8.0, -8.4, -7.2, -8.2, -8.5, -7.9};
 __constant__ double c_nn3_s[16] = {-22.2, -22.4, -21.0, -20.4, -22.7, -19.9, -27.2, -21.0, -22.2, -24.4, -19.9, -22.4, -21.3, -22.2, -22.7, -22.2};
 
+// MeltingTemp._check(seq, "Tm_NN") keeps A, C, G, T (U is back-transcribed to T) and I, and DROPS
+// every other character (N and the other ambiguity codes included) before anything is summed --
+// the reference calls Tm_NN(seq, strict=False), so nothing raises.  4 = inosine: stays in the
+// sequence, but its neighbour pairs are in no table (strict=False: skipped) and it is not an
+// A/T/G/C end.  -1 = dropped.
 __device__ __forceinline__ int ascii_code(char ch) {
     switch (ch) {
         case 'A': case 'a': return 0;
         case 'C': case 'c': return 1;
         case 'G': case 'g': return 2;
-        case 'T': case 't': case 'U': case 'u': return 3;  // _check() maps U to T
+        case 'T': case 't': case 'U': case 'u': return 3;
+        case 'I': case 'i': return 4;
     }
     return -1;
 }
@@ -287,44 +293,38 @@ __global__ void k_tm_nn(const char* __restrict__ ascii, const long long* __restr
     if (t >= n) return;
     const char* s = ascii + off[t];
     const int len = (int)(off[t + 1] - off[t]);
-    double dh = 0.0, ds = 0.0;
-    bool bad = len < 1;
-    int first = 0, last = 0, prev = 0;
+    int kept = 0, first = -1, last = -1;
     for (int k = 0; k < len; ++k) {
         const int c = ascii_code(s[k]);
-        if (c < 0) {
-            bad = true;
-            break;
-        }
-        if (k == 0) first = c;
-        else {  // the 'zipping': nearest-neighbour sum along the sequence
-            dh += c_nn3_h[4 * prev + c];
-            ds += c_nn3_s[4 * prev + c];
-        }
-        prev = c;
+        if (c < 0) continue;
+        if (first < 0) first = c;
         last = c;
+        ++kept;
     }
-    if (bad) {
+    if (kept == 0) {   // Biopython: IndexError on seq[0]
         tm[t] = nan("");
         return;
     }
     // Biopython adds the initiation terms BEFORE zipping; addition order matters for the
-    // last bit, so rebuild the sums in its order: init terms first, then the dinucleotides.
+    // last bit: init terms first, then the dinucleotides.
     const int at = (first == 0 || first == 3) + (last == 0 || last == 3);
-    const int gc = 2 - at;
+    const int gc = (first == 1 || first == 2) + (last == 1 || last == 2);
     double h = 0.0, sS = 0.0;
     h += 2.3 * at;
     sS += 4.1 * at;
     h += 0.1 * gc;
     sS += -2.8 * gc;
-    prev = first;
-    for (int k = 1; k < len; ++k) {
+    int prev = -1;
+    for (int k = 0; k < len; ++k) {
         const int c = ascii_code(s[k]);
-        h += c_nn3_h[4 * prev + c];
-        sS += c_nn3_s[4 * prev + c];
+        if (c < 0) continue;
+        if (prev >= 0 && prev < 4 && c < 4) {  // the 'zipping': nearest-neighbour sum along the kept bases
+            h += c_nn3_h[4 * prev + c];
+            sS += c_nn3_s[4 * prev + c];
+        }
         prev = c;
     }
-    const double corr = 0.368 * (len - 1) * K.log_mon;
+    const double corr = 0.368 * (kept - 1) * K.log_mon;
     sS += corr;
     tm[t] = (1000 * h) / (sS + K.r_log_k) - 273.15;
 }

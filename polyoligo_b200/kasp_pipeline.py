@@ -15,9 +15,9 @@ stage works on flat numpy arrays and batched C-ABI calls, nothing is per-marker 
                                              po_annotate_mutations_batch, po_rank_pairs_batch
 
 Scope notes: templates are plain ACGT of one common length (<= 512), alleles are SNPs or
-indels <= 32 nt, the given marker primer is taken at its true template position (the
-reference's designPrimers locates it with a string search, which is the same position unless
-the primer occurs twice in the template), and BLAST off-targets are fixed to none.
+indels <= 32 nt, the given marker primer is located like the reference's designPrimers does it
+(first occurrence of its sequence in the template; po_p3_design_fixed_batch relocates the task),
+and BLAST off-targets are fixed to none.
 """
 import os
 import threading
@@ -145,6 +145,8 @@ def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk
     vparams = lib_primer3.valid_params()
     templates = np.ascontiguousarray(data["templates"], dtype=np.uint8)
     n, length = templates.shape
+    if 2 * (hi - lo + 1) > 32:
+        raise ValueError("PRIMER_MAX_SIZE - PRIMER_MIN_SIZE + 1 > 16: the merge keys hold 32 marker-primer slots")
     out = {k: [] for k in ("f", "r", "a", "dir", "goodness", "qbits", "sel", "n_sel", "count")}
     types_ = ["mism_mut", "mism", "partial_mism_mut", "partial_mism", "all_mut", "all"] \
         if data.get("mut_seg") is not None else ["mism", "partial_mism", "all"]

@@ -275,9 +275,22 @@ def rank_batch(pcrs, n, assay_name, device=None, reporters=None):
         return
     n_off, aaf, indel = _rank_inputs(pps, keys)
     kw = {}
+    if len({float(pp.tm_delta) for pp in pps}) != 1:
+        raise ValueError("rank_batch: tm_delta differs between the pairs of one batch")
     if kasp:
         kw["a"] = _native.pack([pp.primers["A"].sequence for pp in pps])
         kw["direction"] = np.array([0 if pp.dir == "F" else 1 for pp in pps], dtype=np.uint8)
+        # The tails are the ones add_reporter_dyes put on the primers (reference _lib_kasp.py:75-86,
+        # 95-97: reporter + sequence): marker primer -> reporters[0], ALT -> reporters[1], common -> "".
+        on_primers = {(pp.primers[pp.dir].reporter, pp.primers["A"].reporter) for pp in pps}
+        if len(on_primers) != 1:
+            raise ValueError("rank_batch: the pairs of one batch carry different reporter dyes")
+        own = on_primers.pop()
+        if reporters is None:
+            reporters = own if any(own) else None
+        elif any(own) and tuple(reporters) != own:
+            raise ValueError("rank_batch: reporters argument %r conflicts with the primers' reporter dyes %r"
+                             % (tuple(reporters), own))
         kw["reporters"] = reporters
     if assay_name == "HRM":
         kw["hrm_delta"] = np.array([pp.hrm["delta"] for pp in pps])
@@ -403,7 +416,7 @@ def hrm_temps_batch(ref_products, alt_products, device=None):
     out = []
     for r, a in zip(tm[:n], tm[n:]):
         if np.isnan(r) or np.isnan(a):
-            raise ValueError("Base not allowed for Tm_NN")          # what Biopython raises
+            raise IndexError("string index out of range")   # Biopython: no A/C/G/T/I base left after _check()
         out.append({"ref": lib_utils.round_tidy(r, 4), "alt": lib_utils.round_tidy(a, 4),
                     "delta": lib_utils.round_tidy(np.abs(r - a), 2)})
     return out

@@ -20,16 +20,30 @@ _lock = threading.Lock()
 _contexts = {}
 
 
-def get_context(device=None):
+DEFAULT_CONDITIONS = (50.0, 0.0, 0.8, 50.0, 37.0, 30, 60)   # primer3-py 0.6.0 ThermoAnalysis() defaults
+
+
+def get_context(device=None, conditions=None):
     """Process-wide scoring context, created lazily (after any fork: the reference
-    forks one worker per marker, reference src/polyoligo/cli_kasp.py:354)."""
+    forks one worker per marker, reference src/polyoligo/cli_kasp.py:354).
+
+    One context per (process, device, conditions): the ``conditions=None`` context keeps the
+    ``ThermoAnalysis()`` defaults for ever -- it is the one ``lib_primer3`` / ``kasp`` use, like the
+    reference, which builds a fresh default ``ThermoAnalysis()`` per call -- and a non-default
+    ``ThermoAnalysis(mv_conc=...)`` gets its own context instead of mutating the shared one."""
     if device is None:
         device = int(os.environ.get("POLYOLIGO_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-    key = (os.getpid(), device)
+    if conditions is not None:
+        conditions = tuple(conditions)
+        if conditions == DEFAULT_CONDITIONS:
+            conditions = None
+    key = (os.getpid(), device, conditions)
     with _lock:
         ctx = _contexts.get(key)
         if ctx is None:
             ctx = _native.Context(device)
+            if conditions is not None:
+                ctx.set_conditions(*conditions)
             _contexts[key] = ctx
         return ctx
 
@@ -65,10 +79,9 @@ class ThermoAnalysis:
         self._device = device
 
     def _ctx(self):
-        ctx = get_context(self._device)
-        ctx.set_conditions(self.mv_conc, self.dv_conc, self.dntp_conc, self.dna_conc, self.temp_c, self.max_loop,
-                           self.max_nn_length)
-        return ctx
+        return get_context(self._device, (float(self.mv_conc), float(self.dv_conc), float(self.dntp_conc),
+                                          float(self.dna_conc), float(self.temp_c), int(self.max_loop),
+                                          int(self.max_nn_length)))
 
     @staticmethod
     def _check(seqs):
@@ -132,4 +145,4 @@ def gc_content(seq):
 
 
 __all__ = ["ThermoAnalysis", "ThermoResult", "calcTm", "calcHairpin", "calcHomodimer", "calcHeterodimer",
-           "get_context", "gc_content", "np"]
+           "get_context", "gc_content"]

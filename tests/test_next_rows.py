@@ -15,8 +15,12 @@ def test_tm_nn_oracle_biopython_doc_anchor():
     # Biopython tutorial / MeltingTemp docstring: Tm_NN('CGTTCCAAAGATGTGGGCATGAGCTTAC') prints 60.32
     from oracle.polyoligo_oracle import tm_nn
     assert "%0.2f" % tm_nn("CGTTCCAAAGATGTGGGCATGAGCTTAC") == "60.32"
+    # Tm_NN(seq, strict=False) as the reference calls it (lib_markers.py:586-587): _check() DROPS
+    # ambiguous bases, it does not raise -- an N-padded product still gets its temperatures
+    assert tm_nn("ACGTNACGTRY") == tm_nn("ACGTACGT")
+    assert tm_nn("nnACGuACGT") == tm_nn("ACGTACGT")
     with pytest.raises(ValueError):
-        tm_nn("ACGTNACGT")
+        tm_nn("NNNN")
 
 
 def test_annotate_mutations_oracle_matches_reference_fixture():
@@ -37,7 +41,9 @@ def test_tm_nn_kernel_matches_oracle(ctx):
     got = ctx.tm_nn_batch(seqs)
     assert np.array_equal(got, np.array([tm_nn(s) for s in seqs]))
     assert "%0.2f" % got[3000] == "60.32"
-    assert np.isnan(ctx.tm_nn_batch(["ACGTNACGT", "ACGT"])[0])
+    odd = ["ACGTNACGTRY", "NNACGTACGTNN", "ACGTIACGT", "IACGTACG", "nnacgu", "N" * 30 + seqs[0] + "N" * 30]
+    assert np.array_equal(ctx.tm_nn_batch(odd), np.array([tm_nn(s) for s in odd]))
+    assert np.isnan(ctx.tm_nn_batch(["NNNN", "ACGT"])[0])
     from polyoligo_b200 import lib_primer3 as lp
     out = lp.hrm_temps_batch(seqs[:5], [s[:20] + ("A" if s[20] != "A" else "C") + s[21:] for s in seqs[:5]])
     assert all(set(o) == {"ref", "alt", "delta"} and o["delta"] >= 0 for o in out)

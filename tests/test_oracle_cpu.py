@@ -62,19 +62,44 @@ def test_calctm_invalid_and_long(oracle):
     assert oracle.calcTm(long_seq) == expect
 
 
-def test_hairpin_readme_anchor(oracle):
-    # primer3-py README: calcHairpin('CCCCCATCCGATCAGGGGG') ->
-    #   structure_found=True, tm=34.15, dg=337.09, dh=-36300.00, ds=-118.13
-    # Structure and dH (4 CC/GG stacks + CA/GA terminal mismatch) are reproduced.
-    # dS / Tm depend on upstream's tstack2.ds / loops.ds files, which are not
-    # available offline: the literature table set gives -108.11 (PARITY UNPINNED,
-    # see oracle/po_oracle.h and DESIGN.md).
-    r = oracle.calcHairpin("CCCCCATCCGATCAGGGGG")
+README_HAIRPIN = "CCCCCATCCGATCAGGGGG"   # primer3-py README: tm=34.15, dg=337.09, dh=-36300.00, ds=-118.13
+
+
+def _anchor_oracle(oracle):
+    """The oracle on upstream's primer3_config/ tables when POLYOLIGO_P3_CONFIG points at them,
+    else on the embedded literature tables."""
+    d = os.environ.get("POLYOLIGO_P3_CONFIG")
+    if d:
+        from oracle.oracle import Oracle
+        return Oracle(d)
+    return oracle
+
+
+def test_hairpin_readme_anchor_structure_and_dh(oracle):
+    # The part of the only published thal anchor that the literature tables DO reproduce:
+    # same structure (5 bp stem, 9 nt loop) and dH = 4 CC/GG stacks + the CA/GA terminal
+    # mismatch = -36300 exactly; dg / tm are consistent with the reported ds.
+    r = _anchor_oracle(oracle).calcHairpin(README_HAIRPIN)
     assert r.structure_found == 1
     assert r.dh == -36300.0
     assert abs(r.dg - (r.dh - 310.15 * r.ds)) < 1e-9
     assert abs(r.tm - (r.dh / r.ds - 273.15)) < 1e-9
-    assert r.ds == pytest.approx(-108.10728843, abs=1e-6)
+
+
+@pytest.mark.xfail(condition=not os.environ.get("POLYOLIGO_P3_CONFIG"), strict=True,
+                   reason="thal PARITY UNPINNED: embedded literature tables give ds=-108.11 / tm=62.63; upstream's "
+                          "tstack2.ds / loops.ds are not available offline (scripts/localise_anchor.py names the "
+                          "entries).  Passes -- and, being strict, demands removal of this mark -- the moment "
+                          "the real primer3_config/ tables are the default; with POLYOLIGO_P3_CONFIG=<dir> it "
+                          "is a plain assertion.")
+def test_hairpin_readme_anchor_upstream_values(oracle):
+    # upstream's published numbers at print precision (2 dp)
+    r = _anchor_oracle(oracle).calcHairpin(README_HAIRPIN)
+    assert r.structure_found == 1
+    assert round(r.tm, 2) == 34.15
+    assert round(r.dg, 2) == 337.09
+    assert round(r.dh, 2) == -36300.00
+    assert round(r.ds, 2) == -118.13
 
 
 def test_default_tables_match_literature_spot_checks(oracle):

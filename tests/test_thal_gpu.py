@@ -6,6 +6,8 @@ to reproduce the scalar algorithm's IEEE-double arithmetic operation for
 operation, so these tests demand BIT-EXACT tm/dg/dh/ds, which implies the
 tolerances above.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -94,10 +96,32 @@ def test_tm_and_gc(ctx, oracle):
     assert np.array_equal(gc, expect_gc)
 
 
+def _anchor_ctx(ctx):
+    d = os.environ.get("POLYOLIGO_P3_CONFIG")
+    return (po.Context(0, d), True) if d else (ctx, False)
+
+
 def test_readme_hairpin_anchor_structure(ctx):
-    out = ctx.thal_batch(po.THAL_HAIRPIN, po.pack(["CCCCCATCCGATCAGGGGG"]))
+    c, own = _anchor_ctx(ctx)
+    out = c.thal_batch(po.THAL_HAIRPIN, po.pack(["CCCCCATCCGATCAGGGGG"]))
+    if own:
+        c.close()
     assert out["flags"][0] & po.ITEM_STRUCTURE_FOUND
     assert out["dh"][0] == -36300.0
+
+
+@pytest.mark.xfail(condition=not os.environ.get("POLYOLIGO_P3_CONFIG"), strict=True,
+                   reason="thal PARITY UNPINNED: the embedded literature tables miss upstream's ds by 10.02 e.u. "
+                          "(scripts/localise_anchor.py); a plain assertion with POLYOLIGO_P3_CONFIG=<primer3_config>")
+def test_readme_hairpin_anchor_upstream_values(ctx):
+    # primer3-py README: calcHairpin('CCCCCATCCGATCAGGGGG') -> tm=34.15, dg=337.09, dh=-36300.00, ds=-118.13
+    c, own = _anchor_ctx(ctx)
+    out = c.thal_batch(po.THAL_HAIRPIN, po.pack(["CCCCCATCCGATCAGGGGG"]))
+    if own:
+        c.close()
+    assert round(float(out["tm"][0]), 2) == 34.15
+    assert round(float(out["dg"][0]), 2) == 337.09
+    assert round(float(out["ds"][0]), 2) == -118.13
 
 
 def test_skipped_items_and_empty_batch(ctx):
