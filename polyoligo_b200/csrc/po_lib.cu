@@ -13,6 +13,7 @@
 #include "po_common.h"
 #include "po_thal.cuh"
 #include "po_thal_dimer.cuh"
+#include "po_thal_dimer32.cuh"
 #include "po_thal_hairpin.cuh"
 #include "po_pipeline.cuh"
 
@@ -45,19 +46,28 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
 // warps per CTA of the first-tier kernels (2 CTAs per SM; 72 registers per thread).  Measured
 // on B200 (3M config-4 pairs): 13 / 14 warps 227.3 / 206.8 ms vs 12 / 12 warps 229.4 / 210.2 ms.
 #ifndef PO_DIMER_WARPS
-#define PO_DIMER_WARPS 13
+#define PO_DIMER_WARPS 24
 #endif
 #ifndef PO_HAIRPIN_WARPS
 #define PO_HAIRPIN_WARPS 14
 #endif
+#define PO_DIMER32_CAP 256
+template <int CAP, bool COUNT, bool HAIRPIN>
+struct ThalWs {
+    using type = typename std::conditional<
+        HAIRPIN, HairpinWs<CAP>,
+        typename std::conditional<(!COUNT && CAP == PO_DIMER32_CAP), Dimer32Ws<CAP>, DimerWs<CAP>>::type>::type;
+};
 template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS >= 5 ? 2 : 1))
+__global__ void __launch_bounds__(WARPS * 32, ((HAIRPIN && WARPS >= 5) ? 2 : 1))
 k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po_thal_out* __restrict__ out,
        const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
        const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax, int end_mode,
        po_thal_out* __restrict__ out2) {
-    using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
+    // first dimer tier: oligos <= 32 nt, column-sorted fill (po_thal_dimer32.cuh)
+    constexpr bool FAST32 = !HAIRPIN && !COUNT && CAP == PO_DIMER32_CAP;
+    using Ws = typename ThalWs<CAP, COUNT, HAIRPIN>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem);
     SmemExtra* xt = reinterpret_cast<SmemExtra*>(smem + sizeof(SmemTables));
@@ -96,12 +106,33 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
             po_base_counts(oa, po_len(oa), a1, c1, g1, t1);
             po_base_counts(ob, po_len(ob), a2, c2, g2, t2);
             const int ncell = a1 * t2 + c1 * g2 + g1 * c2 + t1 * a2;
-            if (ncell > CAP) {
-                if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
-                continue;
+            if constexpr (FAST32) {
+                const int len1 = po_len(oa), len2 = po_len(ob);
+                if (po_bad(oa) || po_bad(ob) || len1 == 0 || len2 == 0) {
+                    if (lane == 0) {
+                        po_thal_out r;
+                        r.tm = r.dg = r.dh = r.ds = 0.0;
+                        r.flags = PO_ITEM_SKIPPED;
+                        r.align_end_1 = r.align_end_2 = -1;
+                        out[item] = r;
+                        if (out2) out2[item] = r;
+                    }
+                    continue;
+                }
+                if (ncell > CAP || len1 > 32 || len2 > 32) {
+                    if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
+                    continue;
+                }
+                thal_dimer32_warp<PO_DIMER_GROUP, CAP>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item,
+                                                       out2 ? out2 + item : nullptr);
+            } else {
+                if (ncell > CAP) {
+                    if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
+                    continue;
+                }
+                thal_dimer_warp<PO_DIMER_GROUP, CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item,
+                                                            out2 ? out2 + item : nullptr, relax);
             }
-            thal_dimer_warp<PO_DIMER_GROUP, CAP, COUNT>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item,
-                                                        out2 ? out2 + item : nullptr, relax);
         }
     }
 }
@@ -391,7 +422,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
                        unsigned long long* work, const long long* list, const unsigned long long* list_n,
                        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax,
                        int end_mode = 0, po_thal_out* out2 = nullptr) {
-    using Ws = typename std::conditional<HAIRPIN, HairpinWs<CAP>, DimerWs<CAP>>::type;
+    using Ws = typename ThalWs<CAP, COUNT, HAIRPIN>::type;
     const size_t smem = sizeof(SmemTables) + sizeof(SmemExtra) + WARPS * sizeof(Ws);
     auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -454,14 +485,12 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
         ctx->err = "po_thal: the fused ANY + END1 form needs type ANY";
         return PO_E_INVALID;
     }
-    if (cap == 192) rc = launch_thal<192, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
-    else if (cap == 320) rc = launch_thal<320, 12, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
-    else rc = launch_thal<256, PO_DIMER_WARPS, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
+    rc = launch_thal<256, PO_DIMER_WARPS, COUNT, false>(ctx, st, A, B, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx, em, out2);
     if (rc) return rc;
     // reporter-tailed KASP pairs (<= 47 x 26 nt, ~230-400 finite cells) mostly land in the second tier
-    if ((rc = launch_thal<384, 9, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em, out2))) return rc;
+    if ((rc = launch_thal<384, 18, COUNT, false>(ctx, st, A, B, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx, em, out2))) return rc;
     // l1 is fully consumed by now: its storage takes the third tier's overflow (own counter)
-    if ((rc = launch_thal<768, 5, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em, out2))) return rc;
+    if ((rc = launch_thal<768, 10, COUNT, false>(ctx, st, A, B, n, out, ctr + 4, l2, ctr + 3, l1, ctr + 5, rx, em, out2))) return rc;
     return launch_thal<3600, 2, COUNT, false>(ctx, st, A, B, n, out, ctr + 6, l1, ctr + 5, l2, ctr + 3, rx, em, out2);
 }
 

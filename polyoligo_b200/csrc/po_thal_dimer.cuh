@@ -17,8 +17,8 @@ struct DimerCellCtx {
 
 // upstream calc_bulge_internal(pi, pj, ci, cj): value {dH,dS} of reaching the
 // cell through the loop that starts at list entry kp; {inf,-1} when rejected.
-template <int CAP>
-__device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const DimerWs<CAP>& ws, const double2* ycell,
+template <class WS>
+__device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const WS& ws, const double2* ycell,
                                                     const DimerCellCtx& c, int kp, int* key_out) {
     const uint32_t code = ws.code[kp];
     const double2 pv = ws.cell[kp];
@@ -46,8 +46,8 @@ __device__ __forceinline__ double2 dimer_loop_value(const TabAddr& A, const Dime
 // ci-1-l1; the row's candidates are one contiguous range of the row-major list.
 // Fills the group's run table and cell-side loop operands (ycell, stored
 // identically by every lane of the group) and returns the number of candidates.
-template <int G, int CAP>
-__device__ __forceinline__ int dimer_build_runs(const Grp<G>& g, const SmemTables& tb, DimerWs<CAP>& ws, int ci, int cj,
+template <int G, class WS>
+__device__ __forceinline__ int dimer_build_runs(const Grp<G>& g, const SmemTables& tb, WS& ws, int ci, int cj,
                                                 int max_loop, bool prune, DimerCellCtx* ctx) {
     const int cb = ws.s1[ci], c2 = ws.s2[cj];
     const int q = quad(c2, ws.s2[cj - 1], cb, ws.s1[ci - 1]);
@@ -92,8 +92,8 @@ __device__ __forceinline__ int dimer_build_runs(const Grp<G>& g, const SmemTable
 
 // Forward scan of the group's candidates: every lane keeps its best (largest T,
 // earliest key).  `trip_total` is the warp-wide maximum candidate count.
-template <int G, int CAP>
-__device__ __forceinline__ void dimer_scan(const Grp<G>& g, const TabAddr& A, const DimerWs<CAP>& ws,
+template <int G, class WS>
+__device__ __forceinline__ void dimer_scan(const Grp<G>& g, const TabAddr& A, const WS& ws,
                                            const DimerCellCtx& c, int total, int trip_total, double iH, double iS,
                                            double RC, int mode, double* bT, int* bKey, double2* bV) {
     const RunTable& rt = ws.runs[g.idx];
@@ -106,7 +106,7 @@ __device__ __forceinline__ void dimer_scan(const Grp<G>& g, const TabAddr& A, co
         const int t = t0 + g.lane;
         bool act = t < total;
         int key;
-        const double2 v = dimer_loop_value<CAP>(A, ws, yc, c, run_lookup(rt, act ? t : 0, half), &key);
+        const double2 v = dimer_loop_value(A, ws, yc, c, run_lookup(rt, act ? t : 0, half), &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
         if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
@@ -261,7 +261,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
             const int k = valid ? k0 + g.idx : re - 1;
             const int j = CODE_J(ws.code[k]);
             DimerCellCtx c;
-            int total = dimer_build_runs<G, CAP>(g, tb, ws, i, j, max_loop, !COUNT, &c);
+            int total = dimer_build_runs<G>(g, tb, ws, i, j, max_loop, !COUNT, &c);
             total = valid ? total : 0;
             if (COUNT) cnt += (g.lane == 0) ? total : 0;
             const int trip_total = NG == 1 ? total : warp_max_int(total);
@@ -271,7 +271,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                 double bT, wT = -PO_INF;
                 int bKey, wKey = KEY_NONE;
                 double2 bV;
-                dimer_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
+                dimer_scan<G>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_ALL, &bT, &bKey, &bV);
                 int src = g.argmax(bT, bKey, &wT, &wKey);
                 const bool star = src >= 0 && wKey == KEY_STAR;
                 if (__any_sync(FULL, star)) {
@@ -281,7 +281,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                     double pT, qT = -PO_INF;
                     int pKey, qKey = KEY_NONE;
                     double2 pV;
-                    dimer_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
+                    dimer_scan<G>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_BEFORE_STAR, &pT, &pKey, &pV);
                     const int psrc = g.argmax(pT, pKey, &qT, &qKey);
                     const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
                     const bool redo = star && !((wT - Tm) >= PO_SMALL_NON_ZERO && wT > Tm);
@@ -289,7 +289,7 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
                         double nT, xT = -PO_INF;
                         int nKey, xKey = KEY_NONE;
                         double2 nV;
-                        dimer_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_NO_STAR, &nT, &nKey, &nV);
+                        dimer_scan<G>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_NO_STAR, &nT, &nKey, &nV);
                         const int nsrc = g.argmax(nT, nKey, &xT, &xKey);
                         if (redo) {
                             bV = nV;
@@ -388,13 +388,13 @@ __device__ void thal_dimer_warp(const SmemTables& tb, const SmemExtra& X, const 
         // loops: first candidate in upstream order whose value reproduces the cell
         const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
         DimerCellCtx c;
-        const int total = dimer_build_runs<32, CAP>(gw, tb, ws, i, j, max_loop, true, &c);
+        const int total = dimer_build_runs<32>(gw, tb, ws, i, j, max_loop, true, &c);
         int myKey = KEY_NONE;
         for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
             const bool act = t < total;
             int key;
-            const double2 v = dimer_loop_value<CAP>(A, ws, ws.ycell[0], c, run_lookup(ws.runs[0], act ? t : 0, i - 1 <= 16), &key);
+            const double2 v = dimer_loop_value(A, ws, ws.ycell[0], c, run_lookup(ws.runs[0], act ? t : 0, i - 1 <= 16), &key);
             const double T1 = po_div(v.x + iH, (v.y + iS) + RC);
             // traceback mode of the 1x1 branch reports its value only when T1 >= T2
             const bool ok = act & (key < myKey) & ((key != KEY_STAR) | (T1 >= Tcur));

@@ -1,7 +1,7 @@
 """One-off soak: GPU thal vs the CPU oracle, bit-exact, on a few million random inputs."""
 import sys, time
 import numpy as np
-sys.path.insert(0, "tests")
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import polyoligo_b200 as po
 from polyoligo_b200 import synth
 from oracle.oracle import Oracle
