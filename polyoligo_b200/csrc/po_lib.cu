@@ -52,6 +52,9 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
 #define PO_HAIRPIN_WARPS 14
 #endif
 #define PO_DIMER32_CAP 256
+#ifndef PO_DIMER32_GROUP
+#define PO_DIMER32_GROUP 8
+#endif
 template <int CAP, bool COUNT, bool HAIRPIN>
 struct ThalWs {
     using type = typename std::conditional<
@@ -123,7 +126,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                     if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
                     continue;
                 }
-                thal_dimer32_warp<PO_DIMER_GROUP, CAP>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item,
+                thal_dimer32_warp<PO_DIMER32_GROUP, CAP>(*tb, *xt, TA, ws, oa, ob, K, end_mode != 0, out + item,
                                                        out2 ? out2 + item : nullptr);
             } else {
                 if (ncell > CAP) {
