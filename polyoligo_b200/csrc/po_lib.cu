@@ -15,6 +15,7 @@
 #include "po_thal_dimer.cuh"
 #include "po_thal_dimer32.cuh"
 #include "po_thal_hairpin.cuh"
+#include "po_thal_hairpin32.cuh"
 #include "po_pipeline.cuh"
 
 // ============================================================================
@@ -49,25 +50,36 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
 #define PO_DIMER_WARPS 24
 #endif
 #ifndef PO_HAIRPIN_WARPS
-#define PO_HAIRPIN_WARPS 14
+#define PO_HAIRPIN_WARPS 24
 #endif
 #define PO_DIMER32_CAP 256
 #ifndef PO_DIMER32_GROUP
 #define PO_DIMER32_GROUP 8
 #endif
+#define PO_HAIRPIN32_CAP 128
+#ifndef PO_HAIRPIN_CHUNK
+#define PO_HAIRPIN_CHUNK (1ll << 20)  // hairpins per fill / finish kernel pair: 2 KB of cell values each
+#endif
+#ifndef PO_HAIRPIN32_GROUP
+#define PO_HAIRPIN32_GROUP 8
+#endif
 template <int CAP, bool COUNT, bool HAIRPIN>
 struct ThalWs {
     using type = typename std::conditional<
-        HAIRPIN, HairpinWs<CAP>,
+        HAIRPIN,
+        typename std::conditional<(!COUNT && CAP == PO_HAIRPIN32_CAP), Hairpin32Ws<CAP>, HairpinWs<CAP>>::type,
         typename std::conditional<(!COUNT && CAP == PO_DIMER32_CAP), Dimer32Ws<CAP>, DimerWs<CAP>>::type>::type;
 };
-template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
-__global__ void __launch_bounds__(WARPS * 32, ((HAIRPIN && WARPS >= 5) ? 2 : 1))
+// PHASE (first hairpin tier only): 0 = whole evaluation, 1 = table fill writing the cell values to
+// `cells`, 2 = finish from `cells` (see thal_hairpin32_warp).  `first`: items are first .. first+n-1
+// when no list is given (sub-batches of one call share the overflow list).
+template <int CAP, int WARPS, bool COUNT, bool HAIRPIN, int PHASE = 0>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po_thal_out* __restrict__ out,
        const PoTables* __restrict__ gt, const PoConsts K, unsigned long long* work,
        const long long* __restrict__ list, const unsigned long long* __restrict__ list_n,
        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax, int end_mode,
-       po_thal_out* __restrict__ out2) {
+       po_thal_out* __restrict__ out2, long long first = 0, double2* __restrict__ cells = nullptr) {
     // first dimer tier: oligos <= 32 nt, column-sorted fill (po_thal_dimer32.cuh)
     constexpr bool FAST32 = !HAIRPIN && !COUNT && CAP == PO_DIMER32_CAP;
     using Ws = typename ThalWs<CAP, COUNT, HAIRPIN>::type;
@@ -86,18 +98,38 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
         if (lane == 0) t = atomicAdd(work, 1ull);
         t = __shfl_sync(FULL, t, 0);
         if (t >= total) break;
-        const long long item = list ? list[t] : (long long)t;
+        const long long item = list ? list[t] : first + (long long)t;
         uint4 oa = A[item];
         // upper bound of the finite-cell count: exact count is cheap from base composition
         if constexpr (HAIRPIN) {
             int a, c, g, t_;
             po_base_counts(oa, po_len(oa), a, c, g, t_);
             const int ub = a * t_ + c * g;
-            if (ub > CAP) {
-                if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
-                continue;
+            if constexpr (!COUNT && CAP == PO_HAIRPIN32_CAP) {
+                const int len = po_len(oa);
+                if (po_bad(oa) || len == 0) {
+                    if (lane == 0 && PHASE != 2) {
+                        po_thal_out r;
+                        r.tm = r.dg = r.dh = r.ds = 0.0;
+                        r.flags = PO_ITEM_SKIPPED;
+                        r.align_end_1 = r.align_end_2 = 0;
+                        out[item] = r;
+                    }
+                    continue;
+                }
+                if (ub > CAP || len > 32) {
+                    if (lane == 0 && PHASE != 2) overflow[atomicAdd(overflow_n, 1ull)] = item;
+                    continue;
+                }
+                thal_hairpin32_warp<PO_HAIRPIN32_GROUP, CAP, PHASE>(*tb, *xt, TA, gt, ws, oa, K, out + item,
+                                                                    cells ? cells + (size_t)(item - first) * CAP : nullptr);
+            } else {
+                if (ub > CAP) {
+                    if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
+                    continue;
+                }
+                thal_hairpin_warp<PO_HAIRPIN_GROUP, CAP, COUNT>(*tb, *xt, TA, gt, ws, oa, K, out + item, relax);
             }
-            thal_hairpin_warp<PO_HAIRPIN_GROUP, CAP, COUNT>(*tb, *xt, TA, gt, ws, oa, K, out + item, relax);
         } else {
             uint4 ob = B ? B[item] : oa;
             if (end_mode == 2) {  // thal type END2 is END1 with the oligos swapped (upstream thal())
@@ -245,7 +277,7 @@ struct po_ctx {
     int64_t launches = 0;
     int64_t thal_items = 0;  // thal evaluations requested since po_init
     // grow-only device scratch
-    DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow;
+    DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow, hp_cells;
     DevBuf scratch[12];
     DevBuf p3[28];  // primer picking (po_p3.cuh)
     unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
@@ -335,7 +367,8 @@ extern "C" int po_init(int device, const char* param_dir, po_ctx** out) {
 extern "C" void po_destroy(po_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    DevBuf* bufs[] = {&ctx->a, &ctx->b, &ctx->out, &ctx->out2, &ctx->out3, &ctx->tmv, &ctx->gcv, &ctx->props, &ctx->overflow};
+    DevBuf* bufs[] = {&ctx->a, &ctx->b, &ctx->out, &ctx->out2, &ctx->out3, &ctx->tmv, &ctx->gcv, &ctx->props, &ctx->overflow,
+                      &ctx->hp_cells};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     for (DevBuf& sb : ctx->scratch)
@@ -420,14 +453,14 @@ extern "C" int po_unpack(const po_oligo* packed, int64_t n, char* out) {
 // ============================================================================
 // launchers
 // ============================================================================
-template <int CAP, int WARPS, bool COUNT, bool HAIRPIN>
+template <int CAP, int WARPS, bool COUNT, bool HAIRPIN, int PHASE = 0>
 static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4* B, long long n, po_thal_out* out,
                        unsigned long long* work, const long long* list, const unsigned long long* list_n,
                        long long* overflow, unsigned long long* overflow_n, unsigned long long* relax,
-                       int end_mode = 0, po_thal_out* out2 = nullptr) {
+                       int end_mode = 0, po_thal_out* out2 = nullptr, long long first = 0, double2* cells = nullptr) {
     using Ws = typename ThalWs<CAP, COUNT, HAIRPIN>::type;
     const size_t smem = sizeof(SmemTables) + sizeof(SmemExtra) + WARPS * sizeof(Ws);
-    auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN>;
+    auto kern = k_thal<CAP, WARPS, COUNT, HAIRPIN, PHASE>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARPS * 32, smem));
@@ -442,7 +475,7 @@ static int launch_thal(po_ctx* ctx, cudaStream_t st, const uint4* A, const uint4
     }
     if (blocks < 1) blocks = 1;
     kern<<<(unsigned)blocks, WARPS * 32, smem, st>>>(A, B, n, out, ctx->d_tables, ctx->K, work, list, list_n, overflow,
-                                                     overflow_n, relax, end_mode, out2);
+                                                     overflow_n, relax, end_mode, out2, first, cells);
     ctx->launches++;
     CK(cudaGetLastError());
     return PO_OK;
@@ -471,10 +504,25 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
     long long* l1 = (long long*)ctx->overflow.p;
     long long* l2 = l1 + n;
     unsigned long long* rx = ctr + 7;
-    const int cap = ctx->fast_cap;
     if (type == PO_THAL_HAIRPIN) {
-        if (cap == 256) rc = launch_thal<256, 12, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
-        else rc = launch_thal<128, PO_HAIRPIN_WARPS, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+        if constexpr (COUNT) {
+            rc = launch_thal<128, PO_HAIRPIN_WARPS, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 0, nullptr, nullptr, l1, ctr + 1, rx);
+        } else {
+            // first tier in two kernels per sub-batch (fill, finish): the cell values cross HBM in between
+            const long long chunk = PO_HAIRPIN_CHUNK;
+            const long long m0 = n < chunk ? n : chunk;
+            if ((rc = ensure(ctx, ctx->hp_cells, sizeof(double2) * (size_t)PO_HAIRPIN32_CAP * (size_t)m0))) return rc;
+            double2* cells = (double2*)ctx->hp_cells.p;
+            for (long long s = 0; s < n; s += chunk) {
+                const long long m = (n - s) < chunk ? (n - s) : chunk;
+                CK(cudaMemsetAsync(ctr + 0, 0, sizeof(unsigned long long), st));
+                if ((rc = launch_thal<128, PO_HAIRPIN_WARPS, false, true, 1>(ctx, st, A, nullptr, m, out, ctr + 0, nullptr, nullptr,
+                                                                             l1, ctr + 1, rx, 0, nullptr, s, cells))) return rc;
+                CK(cudaMemsetAsync(ctr + 0, 0, sizeof(unsigned long long), st));
+                if ((rc = launch_thal<128, PO_HAIRPIN_WARPS, false, true, 2>(ctx, st, A, nullptr, m, out, ctr + 0, nullptr, nullptr,
+                                                                             l1, ctr + 1, rx, 0, nullptr, s, cells))) return rc;
+            }
+        }
         if (rc) return rc;
         return launch_thal<1024, 8, COUNT, true>(ctx, st, A, nullptr, n, out, ctr + 2, l1, ctr + 1, l2, ctr + 3, rx);
     }

@@ -24,8 +24,8 @@ struct HairpinCellCtx {
 // value (its traceback == 1 form); the forward pass adds that value afterwards
 // in the same association order.  In upstream's sums the closing pair's term
 // comes first, the enclosed pair's second.
-template <int CAP>
-__device__ __forceinline__ double2 hairpin_loop_term(const TabAddr& A, const HairpinWs<CAP>& ws, const double2* ycell,
+template <class WS>
+__device__ __forceinline__ double2 hairpin_loop_term(const TabAddr& A, const WS& ws, const double2* ycell,
                                                      const HairpinCellCtx& c, int kp, int* key_out) {
     const uint32_t code = ws.code[kp];
     const int b = CODE_B(code);
@@ -61,7 +61,7 @@ __device__ __forceinline__ double2 bonus_lookup(const int32_t* keys, const doubl
 
 // upstream calc_hairpin() without its final dG comparison: the hairpin-loop
 // closure value of (i,j); `cur` is the current DP value of the cell.
-__device__ __forceinline__ double2 hairpin_closure(const SmemTables& tb, const SmemExtra& X, const PoTables* gt,
+__device__ __noinline__ double2 hairpin_closure(const SmemTables& tb, const SmemExtra& X, const PoTables* gt,
                                                    const uint8_t* s, int i, int j, double2 cur) {
     const int loopSize = j - i - 1;
     double H, S;
@@ -116,12 +116,12 @@ __device__ __forceinline__ double2 hairpin_closure(const SmemTables& tb, const S
 }
 
 // index of finite cell (i,j) in the list; caller guarantees it is finite
-template <int CAP>
-__device__ __forceinline__ int hp_index(const HairpinWs<CAP>& ws, int i, int j) {
+template <class WS>
+__device__ __forceinline__ int hp_index(const WS& ws, int i, int j) {
     return ws.start[j] + __popcll(HP_COLMASK(ws, j) >> i);
 }
-template <int CAP>
-__device__ __forceinline__ bool hp_finite(const HairpinWs<CAP>& ws, int i, int j) {
+template <class WS>
+__device__ __forceinline__ bool hp_finite(const WS& ws, int i, int j) {
     if (j - i < PO_MIN_HRPN_LOOP + 1 || i < 1) return false;
     return ((ws.mask[3 - ws.s1[j]] >> (i - 1)) & 1ull) != 0;
 }
@@ -131,8 +131,8 @@ __device__ __forceinline__ bool hp_finite(const HairpinWs<CAP>& ws, int i, int j
 // column's candidates are one contiguous range of the list (rows descending).
 // Fills the group's run table and closing-pair loop operands (ycell, stored
 // identically by every lane of the group) and returns the number of candidates.
-template <int G, int CAP>
-__device__ __forceinline__ int hairpin_build_runs(const Grp<G>& g, const SmemTables& tb, HairpinWs<CAP>& ws, int i,
+template <int G, class WS>
+__device__ __forceinline__ int hairpin_build_runs(const Grp<G>& g, const SmemTables& tb, WS& ws, int i,
                                                   int j, int max_loop, bool prune, HairpinCellCtx* ctx) {
     const int bi = ws.s1[i], bj = ws.s1[j];
     const int q = quad(bi, ws.s1[i + 1] & 3, bj, ws.s1[j - 1] & 3);
@@ -176,8 +176,8 @@ __device__ __forceinline__ int hairpin_build_runs(const Grp<G>& g, const SmemTab
 // groups' candidate counts (uniform trip count).  SCAN_LAST_GE selects the LAST
 // candidate (largest key) with T1 >= Tcur, which is what upstream's
 // CBI(traceback = 2) leaves in its output argument.
-template <int G, int CAP>
-__device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, const HairpinWs<CAP>& ws,
+template <int G, class WS>
+__device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, const WS& ws,
                                              const HairpinCellCtx& c, int total, int trip_total, double iH, double iS,
                                              double RC, int mode, double Tcur, double* bT, int* bKey, double2* bV) {
     const RunTable& rt = ws.runs[g.idx];
@@ -190,7 +190,7 @@ __device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, 
         bool act = t < total;
         const int kp = run_lookup(rt, act ? t : 0, G < 32 && c.j - 6 < 16);
         int key;
-        double2 v = hairpin_loop_term<CAP>(A, ws, yc, c, kp, &key);
+        double2 v = hairpin_loop_term(A, ws, yc, c, kp, &key);
         if (mode == SCAN_NO_STAR) act &= key != KEY_STAR;
         if (mode == SCAN_BEFORE_STAR) act &= key < KEY_STAR;
         const double2 pv = ws.cell[kp];
@@ -215,8 +215,8 @@ __device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, 
 // upstream END5_1..END5_4 for position i, all four variants at once: lanes
 // 8g..8g+7 serve variant g+1.  Returns the variant's {H_max, S_max} in every
 // lane of its group.
-template <int CAP>
-__device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinWs<CAP>& ws, int lane, int i,
+template <class WS>
+__device__ __noinline__ double2 end5_all(const SmemTables& tb, const WS& ws, int lane, int i,
                                             double iH, double iS, double RC) {
     const int v = (lane >> 3) + 1, sub = lane & 7;
     const uint8_t* s = ws.s1;
@@ -291,6 +291,213 @@ __device__ __forceinline__ double2 end5_all(const SmemTables& tb, const HairpinW
         }
     }
     return best;
+}
+
+// calc_terminal_bp (END5_1..4), tracebacku and drawHairpin on a filled table; shared by every
+// hairpin tier (WS: HairpinWs<CAP> or Hairpin32Ws<CAP>).  `cnt` carries the relaxation count of the
+// fill (COUNT variant).
+template <class WS, bool COUNT>
+__device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtra& X, const TabAddr& A,
+                                               const PoTables* gt, WS& ws, const int len, const PoConsts& K,
+                                               po_thal_out r, po_thal_out* out, unsigned long long* relax, int cnt) {
+    const int lane = threadIdx.x & 31;
+    const Grp<32> gw = Grp<32>::make();
+    const double iH = 0.0, iS = -0.00000000001, RC = 0.0;
+    const int max_loop = K.max_loop;
+    // ---- calc_terminal_bp --------------------------------------------------------
+    if (lane == 0) {
+        ws.end5[1][0] = ws.end5[1][1] = -1.0;
+        ws.end5[0][0] = ws.end5[0][1] = PO_INF;
+        ws.end5t[0] = ws.end5t[1] = po_div(PO_INF + iH, -1.0 + iS + RC);
+    }
+    __syncwarp();
+    for (int i = 2; i <= len; ++i) {
+        const double hp = ws.end5[0][i - 1], sp = ws.end5[1][i - 1];
+        double hn = hp, sn = sp;
+        // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
+        // upstream's max5() falls through to its last case, which keeps the previous value
+        const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
+        if (any) {
+            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC);
+            const double T1 = ws.end5t[i - 1];
+            const double Tv = po_div(e.x + iH, e.y + iS + RC);
+            const double T2 = gw.shfl(Tv, 0), T3 = gw.shfl(Tv, 8), T4 = gw.shfl(Tv, 16), T5 = gw.shfl(Tv, 24);
+            int mx;
+            if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
+            else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
+            else if (T3 > T4 && T3 > T5) mx = 3;
+            else if (T4 > T5) mx = 4;
+            else mx = 5;
+            if (mx > 1) {
+                const double eh = gw.shfl(e.x, (mx - 2) * 8), es = gw.shfl(e.y, (mx - 2) * 8);
+                const double Gv = eh - (K.temp_k * es);
+                if (Gv < 0.0) {
+                    hn = eh;
+                    sn = es;
+                }
+            }
+        }
+        if (COUNT) cnt += (lane == 0) ? 4 : 0;
+        const double tn = po_div(hn + iH, sn + iS + RC);
+        if (lane == 0) {
+            ws.end5[0][i] = hn;
+            ws.end5[1][i] = sn;
+            ws.end5t[i] = tn;
+        }
+        __syncwarp();
+    }
+    if (COUNT && relax) {
+        __syncwarp();
+        const unsigned total_cnt = __reduce_add_sync(FULL, (unsigned)cnt);
+        if (lane == 0) atomicAdd(relax, (unsigned long long)total_cnt);
+    }
+    double mh = ws.end5[0][len], ms = ws.end5[1][len];
+    if (!fin(mh) || !fin(ms)) {
+        if (lane == 0) *out = r;
+        return;
+    }
+
+    // ---- tracebacku: collect the paired positions ---------------------------------
+    unsigned long long paired = 0ull;
+    int sp_ = 0;
+    if (lane == 0) ws.stk[0] = (1 << 16) | (len << 8);
+    sp_ = 1;
+    __syncwarp();
+    int guard = 0;
+    while (sp_ > 0 && guard++ < 256) {
+        --sp_;
+        const int item = ws.stk[sp_];
+        __syncwarp();
+        int i = (item >> 8) & 255, j = item & 255;
+        if (item >> 16) {
+            // exterior loop: find the structure that ends at or before i
+            while (i > 0 && eq5(ws.end5[1][i], ws.end5[1][i - 1]) && eq5(ws.end5[0][i], ws.end5[0][i - 1])) --i;
+            if (i == 0) continue;
+            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC);
+            const double hi_ = ws.end5[0][i], si_ = ws.end5[1][i];
+            const unsigned match = __ballot_sync(FULL, (lane & 7) == 0 && eq5(si_, e.y) && eq5(hi_, e.x));
+            if (!match) continue;
+            const int v = (__ffs(match) - 1) / 8 + 1;  // upstream's else-if chain: first matching variant only
+            const uint8_t* s = ws.s1;
+            const int q = (v <= 2) ? i : i - 1;
+            int myKey = KEY_NONE;
+            if (q >= 5) {
+                const int ks = ws.start[q], ke = ws.start[q + 1];
+                for (int kc0 = ks; kc0 < ke; kc0 += 32) {
+                    bool act = kc0 + lane < ke;
+                    const int kc = act ? kc0 + lane : ks;
+                    const int p = CODE_I(ws.code[kc]);
+                    const int k = (v == 1 || v == 3) ? p - 1 : p - 2;
+                    act &= k >= 0;
+                    const int kk = act ? k : 0;
+                    const int bp = s[kk + 1] & 3, bp2 = s[kk + 2] & 3, bi = s[i] & 3, bim = s[i - 1] & 3;
+                    double2 x = make_double2(0.0, 0.0);
+                    if (v == 2) x = tb.dangle5[(bi * 4 + bp2) * 4 + bp];
+                    else if (v == 3) x = tb.dangle3[(bim * 4 + bi) * 4 + bp];
+                    else if (v == 4) x = tb.tstack2[quad(bim, bi, bp2, bp)];
+                    const double2 dv = ws.cell[kc];
+                    const double aH = at_h(s[p], s[q]), aS = at_s(s[p], s[q]);
+                    const double hk = ws.end5[0][kk], sk = ws.end5[1][kk];
+                    double s0, h0, s1v, h1v;
+                    if (v == 1) {
+                        s0 = aS + dv.y;
+                        h0 = aH + dv.x;
+                        s1v = sk + aS + dv.y;
+                        h1v = hk + aH + dv.x;
+                    } else {
+                        s0 = aS + x.y + dv.y;
+                        h0 = aH + x.x + dv.x;
+                        s1v = sk + aS + x.y + dv.y;
+                        h1v = hk + aH + x.x + dv.x;
+                    }
+                    // key: smaller k first; bit 0 = continues into the prefix structure
+                    if (act && eq5(si_, s0) && eq5(hi_, h0)) myKey = min(myKey, k * 2);
+                    else if (act && eq5(si_, s1v) && eq5(hi_, h1v)) myKey = min(myKey, k * 2 + 1);
+                }
+            }
+            const int wKey = gw.min_s32(myKey);
+            if (wKey == KEY_NONE) continue;
+            const int k = wKey >> 1;
+            const int p = (v == 1 || v == 3) ? k + 1 : k + 2;
+            if (lane == 0) {
+                // upstream pushes the pair first, then the prefix: the prefix is popped first
+                ws.stk[sp_] = (p << 8) | q;
+                if (wKey & 1) ws.stk[sp_ + 1] = (1 << 16) | (k << 8);
+            }
+            sp_ += 1 + (wKey & 1);
+            __syncwarp();
+        } else {
+            paired |= (1ull << (i - 1)) | (1ull << (j - 1));
+            const int k = hp_index(ws, i, j);
+            const double2 cur = ws.cell[k];
+            // stack
+            if (hp_finite(ws, i + 1, j - 1)) {
+                const double2 pv = ws.cell[hp_index(ws, i + 1, j - 1)];
+                const double2 st = tb.stack[quad(ws.s1[i], ws.s1[i + 1], ws.s1[j], ws.s1[j - 1])];
+                if (eq5(cur.y, st.y + pv.y) && eq5(cur.x, st.x + pv.x)) {
+                    if (lane == 0) ws.stk[sp_] = ((i + 1) << 8) | (j - 1);
+                    ++sp_;
+                    __syncwarp();
+                    continue;
+                }
+            }
+            // hairpin loop closes here
+            const double2 hv = hairpin_closure(tb, X, gt, ws.s1, i, j, cur);
+            if (eq5(cur.y, hv.y) && eq5(cur.x, hv.x)) continue;
+            // bulge / interior loop
+            if (j - i < 7) continue;
+            const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
+            HairpinCellCtx c;
+            const int total = hairpin_build_runs<32>(gw, tb, ws, i, j, max_loop, true, &c);
+            if (total == 0) continue;
+            double bT;
+            int bKey;
+            double2 bV;
+            hairpin_scan<32>(gw, A, ws, c, total, total, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
+            // LAST candidate with T1 >= Tcur: largest key
+            const int mxKey = gw.max_s32(bKey == KEY_NONE ? -1 : bKey);
+            if (mxKey < 0) continue;
+            const unsigned who = __ballot_sync(FULL, bKey == mxKey);
+            const int src = __ffs(who) - 1;
+            double H2 = gw.shfl(bV.x, src), S2 = gw.shfl(bV.y, src);
+            if (fin(H2) && S2 < PO_MIN_ENTROPY_CUTOFF) {
+                S2 = PO_MIN_ENTROPY;
+                H2 = 0.0;
+            }
+            if (!(eq5(cur.y, S2) && eq5(cur.x, H2))) continue;
+            // first candidate (upstream order) whose value reproduces the cell
+            int myKey = KEY_NONE;
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                const bool act = t < total;
+                const int kp = run_lookup(ws.runs[0], act ? t : 0, false);
+                int key;
+                double2 v = hairpin_loop_term(A, ws, ws.ycell[0], c, kp, &key);
+                v = hp_fix(v.x, v.y);  // traceback == 1 form: every branch reports its value
+                const double2 pv = ws.cell[kp];
+                if (act && key < myKey && eq5(cur.y, v.y + pv.y) && eq5(cur.x, v.x + pv.x)) myKey = key;
+            }
+            const int wKey = gw.min_s32(myKey);
+            if (wKey == KEY_NONE) continue;
+            const int sum = wKey >> 6, l1 = wKey & 63;
+            const int ii = i + l1 + 1, jj = j - (sum - l1) - 1;
+            if (lane == 0) ws.stk[sp_] = (ii << 8) | jj;
+            ++sp_;
+            __syncwarp();
+        }
+    }
+
+    // ---- drawHairpin: the count stops before the last base ---------------------------
+    const int N = __popcll(paired & ((1ull << (len - 1)) - 1ull));
+    const double t = (mh / (ms + (((N / 2) - 1) * K.salt_corr))) - PO_ABSOLUTE_ZERO;
+    const double mg = mh - (K.temp_k * (ms + (((N / 2) - 1) * K.salt_corr)));
+    ms = ms + (((N / 2) - 1) * K.salt_corr);
+    r.tm = t;
+    r.dg = mg;
+    r.dh = mh;
+    r.ds = ms;
+    r.flags = PO_ITEM_STRUCTURE_FOUND;
+    if (lane == 0) *out = r;
 }
 
 template <int G, int CAP, bool COUNT>
@@ -370,8 +577,8 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const int i = CODE_I(ws.code[k]);
             double S0 = PO_MIN_ENTROPY, H0 = 0.0;
             const double T0 = T0_const;
-            const bool pfin = hp_finite<CAP>(ws, i + 1, j - 1);
-            double2 pv = ws.cell[pfin ? hp_index<CAP>(ws, i + 1, j - 1) : 0];
+            const bool pfin = hp_finite(ws, i + 1, j - 1);
+            double2 pv = ws.cell[pfin ? hp_index(ws, i + 1, j - 1) : 0];
             if (!pfin) pv = make_double2(PO_INF, -1.0);
             const double2 st = tb.stack[quad(ws.s1[i], ws.s1[i + 1], ws.s1[j], ws.s1[j - 1])];
             double S1 = pv.y + st.y;
@@ -396,7 +603,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
             const int k = valid ? k0 + g.idx : ce - 1;
             const int i = CODE_I(ws.code[k]);
             HairpinCellCtx c;
-            int total = hairpin_build_runs<G, CAP>(g, tb, ws, i, j, max_loop, !COUNT, &c);
+            int total = hairpin_build_runs<G>(g, tb, ws, i, j, max_loop, !COUNT, &c);
             total = valid ? total : 0;
             if (COUNT) cnt += (g.lane == 0) ? total : 0;
             const int trip_total = NG == 1 ? total : warp_max_int(total);
@@ -406,14 +613,14 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
                 double bT, wT = -PO_INF;
                 int bKey, wKey = KEY_NONE;
                 double2 bV;
-                hairpin_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
+                hairpin_scan<G>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_ALL, Tcur, &bT, &bKey, &bV);
                 int src = g.argmax(bT, bKey, &wT, &wKey);
                 const bool star = src >= 0 && wKey == KEY_STAR;
                 if (__any_sync(FULL, star)) {
                     double pT, qT = -PO_INF;
                     int pKey, qKey = KEY_NONE;
                     double2 pV;
-                    hairpin_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey,
+                    hairpin_scan<G>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_BEFORE_STAR, Tcur, &pT, &pKey,
                                          &pV);
                     const int psrc = g.argmax(pT, pKey, &qT, &qKey);
                     const double Tm = (psrc >= 0 && qT > Tcur) ? qT : Tcur;
@@ -422,7 +629,7 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
                         double nT, xT = -PO_INF;
                         int nKey, xKey = KEY_NONE;
                         double2 nV;
-                        hairpin_scan<G, CAP>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_NO_STAR, Tcur, &nT, &nKey,
+                        hairpin_scan<G>(g, A, ws, c, total, trip_total, iH, iS, RC, SCAN_NO_STAR, Tcur, &nT, &nKey,
                                              &nV);
                         const int nsrc = g.argmax(nT, nKey, &xT, &xKey);
                         if (redo) {
@@ -464,198 +671,5 @@ __device__ void thal_hairpin_warp(const SmemTables& tb, const SmemExtra& X, cons
         __syncwarp();
     }
 
-    // ---- calc_terminal_bp --------------------------------------------------------
-    if (lane == 0) {
-        ws.end5[1][0] = ws.end5[1][1] = -1.0;
-        ws.end5[0][0] = ws.end5[0][1] = PO_INF;
-        ws.end5t[0] = ws.end5t[1] = po_div(PO_INF + iH, -1.0 + iS + RC);
-    }
-    __syncwarp();
-    for (int i = 2; i <= len; ++i) {
-        const double hp = ws.end5[0][i - 1], sp = ws.end5[1][i - 1];
-        double hn = hp, sn = sp;
-        // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
-        // upstream's max5() falls through to its last case, which keeps the previous value
-        const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
-        if (any) {
-            const double2 e = end5_all<CAP>(tb, ws, lane, i, iH, iS, RC);
-            const double T1 = ws.end5t[i - 1];
-            const double Tv = po_div(e.x + iH, e.y + iS + RC);
-            const double T2 = gw.shfl(Tv, 0), T3 = gw.shfl(Tv, 8), T4 = gw.shfl(Tv, 16), T5 = gw.shfl(Tv, 24);
-            int mx;
-            if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
-            else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
-            else if (T3 > T4 && T3 > T5) mx = 3;
-            else if (T4 > T5) mx = 4;
-            else mx = 5;
-            if (mx > 1) {
-                const double eh = gw.shfl(e.x, (mx - 2) * 8), es = gw.shfl(e.y, (mx - 2) * 8);
-                const double Gv = eh - (K.temp_k * es);
-                if (Gv < 0.0) {
-                    hn = eh;
-                    sn = es;
-                }
-            }
-        }
-        if (COUNT) cnt += (lane == 0) ? 4 : 0;
-        const double tn = po_div(hn + iH, sn + iS + RC);
-        if (lane == 0) {
-            ws.end5[0][i] = hn;
-            ws.end5[1][i] = sn;
-            ws.end5t[i] = tn;
-        }
-        __syncwarp();
-    }
-    if (COUNT && relax) {
-        __syncwarp();
-        const unsigned total_cnt = __reduce_add_sync(FULL, (unsigned)cnt);
-        if (lane == 0) atomicAdd(relax, (unsigned long long)total_cnt);
-    }
-    double mh = ws.end5[0][len], ms = ws.end5[1][len];
-    if (!fin(mh) || !fin(ms)) {
-        if (lane == 0) *out = r;
-        return;
-    }
-
-    // ---- tracebacku: collect the paired positions ---------------------------------
-    unsigned long long paired = 0ull;
-    int sp_ = 0;
-    if (lane == 0) ws.stk[0] = (1 << 16) | (len << 8);
-    sp_ = 1;
-    __syncwarp();
-    int guard = 0;
-    while (sp_ > 0 && guard++ < 256) {
-        --sp_;
-        const int item = ws.stk[sp_];
-        __syncwarp();
-        int i = (item >> 8) & 255, j = item & 255;
-        if (item >> 16) {
-            // exterior loop: find the structure that ends at or before i
-            while (i > 0 && eq5(ws.end5[1][i], ws.end5[1][i - 1]) && eq5(ws.end5[0][i], ws.end5[0][i - 1])) --i;
-            if (i == 0) continue;
-            const double2 e = end5_all<CAP>(tb, ws, lane, i, iH, iS, RC);
-            const double hi_ = ws.end5[0][i], si_ = ws.end5[1][i];
-            const unsigned match = __ballot_sync(FULL, (lane & 7) == 0 && eq5(si_, e.y) && eq5(hi_, e.x));
-            if (!match) continue;
-            const int v = (__ffs(match) - 1) / 8 + 1;  // upstream's else-if chain: first matching variant only
-            const uint8_t* s = ws.s1;
-            const int q = (v <= 2) ? i : i - 1;
-            int myKey = KEY_NONE;
-            if (q >= 5) {
-                const int ks = ws.start[q], ke = ws.start[q + 1];
-                for (int kc0 = ks; kc0 < ke; kc0 += 32) {
-                    bool act = kc0 + lane < ke;
-                    const int kc = act ? kc0 + lane : ks;
-                    const int p = CODE_I(ws.code[kc]);
-                    const int k = (v == 1 || v == 3) ? p - 1 : p - 2;
-                    act &= k >= 0;
-                    const int kk = act ? k : 0;
-                    const int bp = s[kk + 1] & 3, bp2 = s[kk + 2] & 3, bi = s[i] & 3, bim = s[i - 1] & 3;
-                    double2 x = make_double2(0.0, 0.0);
-                    if (v == 2) x = tb.dangle5[(bi * 4 + bp2) * 4 + bp];
-                    else if (v == 3) x = tb.dangle3[(bim * 4 + bi) * 4 + bp];
-                    else if (v == 4) x = tb.tstack2[quad(bim, bi, bp2, bp)];
-                    const double2 dv = ws.cell[kc];
-                    const double aH = at_h(s[p], s[q]), aS = at_s(s[p], s[q]);
-                    const double hk = ws.end5[0][kk], sk = ws.end5[1][kk];
-                    double s0, h0, s1v, h1v;
-                    if (v == 1) {
-                        s0 = aS + dv.y;
-                        h0 = aH + dv.x;
-                        s1v = sk + aS + dv.y;
-                        h1v = hk + aH + dv.x;
-                    } else {
-                        s0 = aS + x.y + dv.y;
-                        h0 = aH + x.x + dv.x;
-                        s1v = sk + aS + x.y + dv.y;
-                        h1v = hk + aH + x.x + dv.x;
-                    }
-                    // key: smaller k first; bit 0 = continues into the prefix structure
-                    if (act && eq5(si_, s0) && eq5(hi_, h0)) myKey = min(myKey, k * 2);
-                    else if (act && eq5(si_, s1v) && eq5(hi_, h1v)) myKey = min(myKey, k * 2 + 1);
-                }
-            }
-            const int wKey = gw.min_s32(myKey);
-            if (wKey == KEY_NONE) continue;
-            const int k = wKey >> 1;
-            const int p = (v == 1 || v == 3) ? k + 1 : k + 2;
-            if (lane == 0) {
-                // upstream pushes the pair first, then the prefix: the prefix is popped first
-                ws.stk[sp_] = (p << 8) | q;
-                if (wKey & 1) ws.stk[sp_ + 1] = (1 << 16) | (k << 8);
-            }
-            sp_ += 1 + (wKey & 1);
-            __syncwarp();
-        } else {
-            paired |= (1ull << (i - 1)) | (1ull << (j - 1));
-            const int k = hp_index<CAP>(ws, i, j);
-            const double2 cur = ws.cell[k];
-            // stack
-            if (hp_finite<CAP>(ws, i + 1, j - 1)) {
-                const double2 pv = ws.cell[hp_index<CAP>(ws, i + 1, j - 1)];
-                const double2 st = tb.stack[quad(ws.s1[i], ws.s1[i + 1], ws.s1[j], ws.s1[j - 1])];
-                if (eq5(cur.y, st.y + pv.y) && eq5(cur.x, st.x + pv.x)) {
-                    if (lane == 0) ws.stk[sp_] = ((i + 1) << 8) | (j - 1);
-                    ++sp_;
-                    __syncwarp();
-                    continue;
-                }
-            }
-            // hairpin loop closes here
-            const double2 hv = hairpin_closure(tb, X, gt, ws.s1, i, j, cur);
-            if (eq5(cur.y, hv.y) && eq5(cur.x, hv.x)) continue;
-            // bulge / interior loop
-            if (j - i < 7) continue;
-            const double Tcur = po_div(cur.x + iH, (cur.y + iS) + RC);
-            HairpinCellCtx c;
-            const int total = hairpin_build_runs<32, CAP>(gw, tb, ws, i, j, max_loop, true, &c);
-            if (total == 0) continue;
-            double bT;
-            int bKey;
-            double2 bV;
-            hairpin_scan<32, CAP>(gw, A, ws, c, total, total, iH, iS, RC, SCAN_LAST_GE, Tcur, &bT, &bKey, &bV);
-            // LAST candidate with T1 >= Tcur: largest key
-            const int mxKey = gw.max_s32(bKey == KEY_NONE ? -1 : bKey);
-            if (mxKey < 0) continue;
-            const unsigned who = __ballot_sync(FULL, bKey == mxKey);
-            const int src = __ffs(who) - 1;
-            double H2 = gw.shfl(bV.x, src), S2 = gw.shfl(bV.y, src);
-            if (fin(H2) && S2 < PO_MIN_ENTROPY_CUTOFF) {
-                S2 = PO_MIN_ENTROPY;
-                H2 = 0.0;
-            }
-            if (!(eq5(cur.y, S2) && eq5(cur.x, H2))) continue;
-            // first candidate (upstream order) whose value reproduces the cell
-            int myKey = KEY_NONE;
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                const bool act = t < total;
-                const int kp = run_lookup(ws.runs[0], act ? t : 0, false);
-                int key;
-                double2 v = hairpin_loop_term<CAP>(A, ws, ws.ycell[0], c, kp, &key);
-                v = hp_fix(v.x, v.y);  // traceback == 1 form: every branch reports its value
-                const double2 pv = ws.cell[kp];
-                if (act && key < myKey && eq5(cur.y, v.y + pv.y) && eq5(cur.x, v.x + pv.x)) myKey = key;
-            }
-            const int wKey = gw.min_s32(myKey);
-            if (wKey == KEY_NONE) continue;
-            const int sum = wKey >> 6, l1 = wKey & 63;
-            const int ii = i + l1 + 1, jj = j - (sum - l1) - 1;
-            if (lane == 0) ws.stk[sp_] = (ii << 8) | jj;
-            ++sp_;
-            __syncwarp();
-        }
-    }
-
-    // ---- drawHairpin: the count stops before the last base ---------------------------
-    const int N = __popcll(paired & ((1ull << (len - 1)) - 1ull));
-    const double t = (mh / (ms + (((N / 2) - 1) * K.salt_corr))) - PO_ABSOLUTE_ZERO;
-    const double mg = mh - (K.temp_k * (ms + (((N / 2) - 1) * K.salt_corr)));
-    ms = ms + (((N / 2) - 1) * K.salt_corr);
-    r.tm = t;
-    r.dg = mg;
-    r.dh = mh;
-    r.ds = ms;
-    r.flags = PO_ITEM_STRUCTURE_FOUND;
-    if (lane == 0) *out = r;
+    hairpin_finish<HairpinWs<CAP>, COUNT>(tb, X, A, gt, ws, len, K, r, out, relax, cnt);
 }
