@@ -50,7 +50,7 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
 #define PO_DIMER_WARPS 24
 #endif
 #ifndef PO_HAIRPIN_WARPS
-#define PO_HAIRPIN_WARPS 24
+#define PO_HAIRPIN_WARPS 28
 #endif
 #define PO_DIMER32_CAP 256
 #ifndef PO_DIMER32_GROUP

@@ -217,7 +217,7 @@ __device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, 
 // lane of its group.
 template <class WS>
 __device__ __noinline__ double2 end5_all(const SmemTables& tb, const WS& ws, int lane, int i,
-                                            double iH, double iS, double RC) {
+                                            double iH, double iS, double RC, double T2) {
     const int v = (lane >> 3) + 1, sub = lane & 7;
     const uint8_t* s = ws.s1;
     const int q = (v <= 2) ? i : i - 1;  // paired 3' base
@@ -229,7 +229,6 @@ __device__ __noinline__ double2 end5_all(const SmemTables& tb, const WS& ws, int
     const int n_im = i >= 6 ? ws.start[i] - ws.start[i - 1] : 0;
     const int trips = (max(n_i, n_im) + 7) >> 3;
     const int ks = q >= 5 ? ws.start[q] : 0, ke = q >= 5 ? ws.start[q + 1] : 0;
-    const double T2 = po_div(0 + iH, 0 + iS + RC);
     for (int it = 0; it < trips; ++it) {
         const int kc0 = ks + sub + 8 * it;
         bool act = kc0 < ke;
@@ -270,7 +269,7 @@ __device__ __noinline__ double2 end5_all(const SmemTables& tb, const WS& ws, int
             H = PO_INF;
             S = -1.0;
         }
-        const double T1 = po_div(H + iH, S + iS + RC);
+        const double T1 = po_div_rej(H + iH, S + iS + RC);  // H <= 0 and S <= 0 here, or {inf, -1}
         // upstream keeps the first k with the strictly largest T1; -inf never wins
         if (act & (S > PO_MIN_ENTROPY_CUTOFF) & (T1 > -PO_INF) & ((T1 > bestT) | ((T1 == bestT) & (k < bestKey)))) {
             bestT = T1;
@@ -305,6 +304,7 @@ __device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtr
     const double iH = 0.0, iS = -0.00000000001, RC = 0.0;
     const int max_loop = K.max_loop;
     // ---- calc_terminal_bp --------------------------------------------------------
+    const double T2e = po_div(0 + iH, 0 + iS + RC);  // quotient of the empty 5' prefix, END5_1..4's T2
     if (lane == 0) {
         ws.end5[1][0] = ws.end5[1][1] = -1.0;
         ws.end5[0][0] = ws.end5[0][1] = PO_INF;
@@ -314,13 +314,14 @@ __device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtr
     for (int i = 2; i <= len; ++i) {
         const double hp = ws.end5[0][i - 1], sp = ws.end5[1][i - 1];
         double hn = hp, sn = sp;
+        double tn = ws.end5t[i - 1];  // T of (hn, sn): the previous quotient, or the chosen variant's
         // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
         // upstream's max5() falls through to its last case, which keeps the previous value
         const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
         if (any) {
-            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC);
+            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC, T2e);
             const double T1 = ws.end5t[i - 1];
-            const double Tv = po_div(e.x + iH, e.y + iS + RC);
+            const double Tv = po_div_rej(e.x + iH, e.y + iS + RC);  // {inf, -1}, or dH <= 0 and dS <= 0
             const double T2 = gw.shfl(Tv, 0), T3 = gw.shfl(Tv, 8), T4 = gw.shfl(Tv, 16), T5 = gw.shfl(Tv, 24);
             int mx;
             if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
@@ -330,15 +331,16 @@ __device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtr
             else mx = 5;
             if (mx > 1) {
                 const double eh = gw.shfl(e.x, (mx - 2) * 8), es = gw.shfl(e.y, (mx - 2) * 8);
+                const double et = mx == 2 ? T2 : mx == 3 ? T3 : mx == 4 ? T4 : T5;
                 const double Gv = eh - (K.temp_k * es);
                 if (Gv < 0.0) {
                     hn = eh;
                     sn = es;
+                    tn = et;
                 }
             }
         }
         if (COUNT) cnt += (lane == 0) ? 4 : 0;
-        const double tn = po_div(hn + iH, sn + iS + RC);
         if (lane == 0) {
             ws.end5[0][i] = hn;
             ws.end5[1][i] = sn;
@@ -373,7 +375,7 @@ __device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtr
             // exterior loop: find the structure that ends at or before i
             while (i > 0 && eq5(ws.end5[1][i], ws.end5[1][i - 1]) && eq5(ws.end5[0][i], ws.end5[0][i - 1])) --i;
             if (i == 0) continue;
-            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC);
+            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC, T2e);
             const double hi_ = ws.end5[0][i], si_ = ws.end5[1][i];
             const unsigned match = __ballot_sync(FULL, (lane & 7) == 0 && eq5(si_, e.y) && eq5(hi_, e.x));
             if (!match) continue;
