@@ -119,17 +119,79 @@ def merge_marker_results(parts):
     return out
 
 
-def design_markers_sharded(data, rank, world, dist=None, **kw):
-    """One rank's share of a marker set under torchrun (contiguous, equally sized ranges: every
-    marker of the synthetic set costs about the same); rank 0 receives the merged result when
-    ``dist`` (an initialised torch.distributed, gloo or nccl) is given.  No data-path collective:
-    the only communication is the host-side gather of the results."""
+# per-marker result record of a design: the selected (top-n) primer pairs, 64 bytes each
+SEL_DTYPE = np.dtype([("f", "<u4", (4,)), ("r", "<u4", (4,)), ("a", "<u4", (4,)), ("goodness", "<i4"),
+                      ("qbits", "<i4"), ("dir", "u1"), ("pad", "u1", (7,))])
+assert SEL_DTYPE.itemsize == 64
+
+
+def compact_selection(res, n_primers):
+    """The per-marker results worth sending home: ``(records[n_markers, n_primers], n_sel)``, the
+    selected pairs of every marker in rank order (rows beyond n_sel are zero)."""
+    sel = np.asarray(res["sel"])
+    n = sel.shape[0]
+    out = np.zeros((n, n_primers), dtype=SEL_DTYPE)
+    ok = sel >= 0
+    idx = sel[ok]
+    out["f"][ok] = res["f"]["w"][idx]
+    out["r"][ok] = res["r"]["w"][idx]
+    out["a"][ok] = res["a"]["w"][idx]
+    out["goodness"][ok] = res["goodness"][idx]
+    out["qbits"][ok] = res["qbits"][idx]
+    out["dir"][ok] = res["dir"][idx]
+    return out, np.asarray(res["n_sel"], dtype=np.int32)
+
+
+def gather_selection(records, n_sel, bounds, dist, device=None):
+    """Gather of the per-marker results of all ranks on rank 0, in marker order, as TENSORS (no
+    pickling): every rank contributes one byte tensor padded to the largest shard; with the nccl
+    backend the bytes travel device to device (``device``: this rank's cuda device), with gloo they
+    stay on the host.  ``bounds``: [(start, stop), ...] of every rank's shard.
+    Returns (records[n_total, n_primers], n_sel[n_total]) on rank 0, None elsewhere."""
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    n_primers = records.shape[1]
+    rows = max(e - s for s, e in bounds)
+    row_bytes = n_primers * SEL_DTYPE.itemsize + 4
+    buf = np.zeros((rows, row_bytes), dtype=np.uint8)
+    m = len(n_sel)
+    buf[:m, :row_bytes - 4] = records.view(np.uint8).reshape(m, -1)
+    buf[:m, row_bytes - 4:] = n_sel.astype("<i4").view(np.uint8).reshape(m, 4)
+    on_gpu = dist.get_backend() == "nccl"
+    t = torch.from_numpy(buf)
+    if on_gpu:
+        t = t.pin_memory().to(torch.device("cuda", device if device is not None else torch.cuda.current_device()),
+                              non_blocking=True)
+    bucket = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, bucket, dst=0)
+    if rank != 0:
+        return None
+    parts = [b.cpu().numpy() if on_gpu else b.numpy() for b in bucket]
+    recs, cnts = [], []
+    for (s, e), p in zip(bounds, parts):
+        k = e - s
+        recs.append(np.ascontiguousarray(p[:k, :row_bytes - 4]).view(SEL_DTYPE).reshape(k, n_primers))
+        cnts.append(np.ascontiguousarray(p[:k, row_bytes - 4:]).view("<i4").reshape(k))
+    return np.concatenate(recs), np.concatenate(cnts)
+
+
+def design_markers_sharded(data, rank, world, dist=None, n_primers=10, device=None, timing=None, **kw):
+    """One rank's share of a marker set under torchrun -- the north_star multi-GPU path: a host-side
+    partition of the marker list (contiguous, equally sized ranges: every marker of the synthetic set
+    costs about the same) plus a gather of the per-marker results on rank 0.  No data-path collective.
+    Returns ``(records, n_sel)`` of ALL markers on rank 0 (``compact_selection`` layout), the local
+    share without ``dist``, None on the other ranks.  ``timing`` (dict) receives the shard's own
+    design time in seconds."""
+    import time
     from . import kasp_pipeline
     n = len(data["starts"])
-    lo, hi = shard_bounds(n, rank, world)
-    local = kasp_pipeline.design_markers_arrays(slice_markers(data, lo, hi), **kw)
+    bounds = partition(np.ones(n), world)
+    lo, hi = bounds[rank]
+    t0 = time.perf_counter()
+    local = kasp_pipeline.design_markers_arrays(slice_markers(data, lo, hi), n_primers=n_primers, device=device, **kw)
+    recs, cnt = compact_selection(local, n_primers)
+    if timing is not None:
+        timing["design_s"] = time.perf_counter() - t0
     if dist is None:
-        return local
-    bucket = [None] * world if rank == 0 else None
-    dist.gather_object(local, bucket, dst=0)
-    return merge_marker_results(bucket) if rank == 0 else None
+        return recs, cnt
+    return gather_selection(recs, cnt, bounds, dist, device)

@@ -171,9 +171,15 @@ def _gloo_marker_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     _set_kasp_design_globals()
     data = kp.synth_config5(5, seed=3, length=300)
-    merged = sharding.design_markers_sharded(data, rank, world, dist=dist, n_primers=3, ctx=CpuContext(nthreads=2))
+    timing = {}
+    merged = sharding.design_markers_sharded(data, rank, world, dist=dist, n_primers=3, ctx=CpuContext(nthreads=2),
+                                             timing=timing)
+    assert timing["design_s"] > 0
     if rank == 0:
-        q.put({k: v.tolist() if k not in ("f", "r", "a") else v.tobytes() for k, v in merged.items()})
+        recs, n_sel = merged          # tensor gather (dist.gather of byte tensors), no pickling
+        q.put((recs.tobytes(), n_sel.tolist()))
+    else:
+        assert merged is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -198,8 +204,13 @@ def test_two_rank_gloo_marker_design_matches_single_process():
     data = kp.synth_config5(5, seed=3, length=300)
     one = kp.design_markers_arrays(data, n_primers=3, ctx=CpuContext(nthreads=2))
     assert len(one["f"]) > 5
-    for k, v in one.items():
-        assert got[k] == (v.tobytes() if k in ("f", "r", "a") else v.tolist()), k
+    recs, n_sel = sharding.compact_selection(one, 3)
+    assert recs.shape == (5, 3) and n_sel.sum() > 3
+    assert got == (recs.tobytes(), n_sel.tolist())
+    # the compact records are the selected pairs, in selection order
+    m = int(np.argmax(n_sel > 0))
+    first = one["sel"][m, 0]
+    assert recs[m, 0]["f"].tobytes() == one["f"][first].tobytes() and recs[m, 0]["goodness"] == one["goodness"][first]
     # slicing keeps the mutation segments consistent
     part = sharding.slice_markers(data, 2, 5)
     assert len(part["alt"]) == 3 and part["mut_seg"][0] == 0 and part["mut_seg"][-1] == len(part["mut_pos"])
