@@ -210,8 +210,12 @@ def _design_chunk(ctx, data, c0, c1, templates, length, lo, hi, settings, depth,
     mk, sl = np.nonzero(keep)                             # marker-major, slot order = mpp order
     # ---- search masks (a4): inclusion maps, mutation twins, the marker-window quirk --------------
     size = int(lib_primer3.PRIMER3_GLOBALS["PRIMER_MAX_SIZE"])
-    if (starts - size < 1).any():
-        raise ValueError("regions closer than PRIMER_MAX_SIZE to the chromosome start are not supported here")
+    # _lib_kasp.py:681-684, literally: mmap[min(1, start - size):max(len, start + size)] = True.  `start` is a
+    # GENOME coordinate: the slice is [1:] for every region further than `size` from the chromosome start, [0:]
+    # at start == size, and for a NEGATIVE first index numpy counts from the end ([len + s:], clamped at 0).
+    s_idx = np.minimum(1, starts - size)
+    win_lo = np.where(s_idx >= 0, s_idx, np.maximum(length + s_idx, 0))
+    in_window = np.arange(length)[None, :] >= win_lo[:, None]
     masks = {}
     mut_rows = None
     if data.get("mut_seg") is not None:
@@ -224,7 +228,7 @@ def _design_chunk(ctx, data, c0, c1, templates, length, lo, hi, settings, depth,
         mp = np.array(data["maps"][base][c0:c1], dtype=bool, copy=True)
         if name.endswith("_mut"):
             mp[mut_rows] = False
-        mp[:, 1:] = True                                  # _lib_kasp.py:681-684: slice [min(1, ..):max(len, ..)]
+        mp |= in_window
         masks[name] = (~mp).astype(np.uint8)
     blob = templates.reshape(-1)
     off = np.arange(m + 1, dtype=np.int64) * length
