@@ -228,23 +228,23 @@ def run_config5(args, rank, world, local_rank, barrier, dist, reduce_max):
     tensors; the gather is inside the timed region.  Wall clock per pass, max over ranks."""
     from polyoligo_b200 import kasp_pipeline as kp, sharding
     set_kasp_globals()
-    workers = 2
+    workers = 1
     kctxs = [kp._worker_context(local_rank, slot) for slot in range(workers)]
-    kp.design_markers_arrays(kp.synth_config5(min(4096, max(256, args.markers // world)), seed=1), n_primers=10,
-                             reporters=DYES, device=local_rank, workers=workers)  # warm-up (allocations)
+    kp.design_markers_fused(kp.synth_config5(min(4096, max(256, args.markers // world)), seed=1), n_primers=10,
+                            reporters=DYES, device=local_rank)  # warm-up (allocations)
     data = kp.synth_config5(args.markers, seed=kp.CONFIG5_SEED)      # the same set on every rank; each takes its range
     bounds = sharding.partition(np.ones(args.markers), world)
     pass_ms, shard_s = [], []
     items = launches = 0
     merged = None
     for _ in range(max(1, args.marker_passes)):
-        stats, timing = {}, {}
+        timing = {}
         items0 = sum(c.thal_item_count() for c in kctxs)
         launches0 = sum(c.launch_count() for c in kctxs)
         barrier()
         t0 = time.perf_counter()
         merged = sharding.design_markers_sharded(data, rank, world, dist=dist, n_primers=10, device=local_rank,
-                                                 timing=timing, reporters=DYES, workers=workers, stats=stats)
+                                                 timing=timing, reporters=DYES)
         barrier()
         pass_ms.append(reduce_max((time.perf_counter() - t0) * 1e3))
         shard_s.append(timing["design_s"])
@@ -267,9 +267,10 @@ def run_config5(args, rank, world, local_rank, barrier, dist, reduce_max):
                         "off-targets (BASELINE config 5 shape), contiguous equal shards over %d rank(s)" %
                         (args.markers, world),
             "scaling": "strong",
-            "timing": "host wall clock of one pass: sharding.design_markers_sharded = shard design through "
-                      "kasp_pipeline.design_markers_arrays (host buffers) + gather of the per-marker results on rank 0 "
-                      "(dist.gather of byte tensors); max over ranks; best of %d passes" % len(pass_ms),
+            "timing": "host wall clock of one pass: sharding.design_markers_sharded = input packing + ONE "
+                      "po_kasp_design_batch call per shard (host buffers in, top-10 triples out) + gather of the "
+                      "per-marker results on rank 0 (dist.gather of byte tensors); max over ranks; best of %d passes"
+                      % len(pass_ms),
             "markers_per_s": args.markers / (best * 1e-3), "ms": best, "pass_ms": pass_ms,
             "thal_evaluations_per_s": sum(p[1] for p in per_rank) / (best * 1e-3),
             "thal_evaluations": int(sum(p[1] for p in per_rank)), "gpu_launches": int(sum(p[2] for p in per_rank)),

@@ -232,7 +232,8 @@ int po_rank_pairs_batch(po_ctx *ctx, const po_rank_in *in, const po_rank_out *ou
  * (reference src/polyoligo/lib_markers.py:586-587) from
  * PCRproduct.get_hrm_temps (:518-529).  Products are 40-150 nt, longer than an
  * oligo record, so the input is ASCII: item k = bytes [offsets[k], offsets[k+1]).
- * A sequence with a non-ACGT letter yields NaN (Biopython raises ValueError). */
+ * Like Biopython's _check(), letters other than A/C/G/T/U/I are DROPPED before anything is summed
+ * (the reference calls Tm_NN(seq, strict=False)); NaN only when nothing is left. */
 int po_tm_nn_batch(po_ctx *ctx, const char *ascii, const int64_t *offsets, int64_t n, double *tm);
 
 /* Numeric part of PrimerPair.add_mutations (reference src/polyoligo/
@@ -319,6 +320,53 @@ int po_p3_design_fixed_batch(po_ctx *ctx, const po_p3_settings *s, const char *t
                              const int64_t *set_off, const int32_t *set_target, int64_t n_sets,
                              const po_p3_task *tasks, int64_t n_tasks, const po_valid_params *valid,
                              po_p3_oligo *fixed_out, po_p3_pair *pairs_out, int32_t *n_pairs_out);
+
+/* ---- the KASP design of a marker batch behind one call (rows a3-a9) -------------------------- */
+/* The design part of the reference's per-marker worker, src/polyoligo/_lib_kasp.py:671-743 (main)
+ * with the BLAST off-target search left out (no off-targets): allele-specific candidate
+ * enumeration, validity, the search masks (include_mut_in_included_maps lib_primer3.py:576-593, the
+ * marker window _lib_kasp.py:681-684, get_sequence_excluded_regions lib_primer3.py:596-600), one
+ * designPrimers per marker primer and mask, the round-robin merge (_lib_kasp.py:591-631), mutation
+ * annotation, reporter-tailed heterodimers, score_kasp, classify and prune.  Everything between the
+ * inputs and the top-n triples stays on the device. */
+typedef struct {
+    int32_t min_size, max_size;   /* PRIMER_MIN_SIZE / PRIMER_MAX_SIZE: marker-primer paddings (at most 16 sizes) */
+    int32_t top_n;                /* pairs kept per marker (cli_kasp -n, default 10)                  */
+    int32_t with_mutations;       /* 1: VCF hook on, six search masks (x_mut twins first); 0: three   */
+    double tm_delta;              /* cli_kasp --tm_delta, default 5.0                                 */
+    po_valid_params valid;        /* Primer.is_valid thresholds                                       */
+    po_oligo reporters[2];        /* reporter dyes (cli_kasp.py:65,72); length 0 for none             */
+} po_kasp_design_params;
+
+typedef struct {
+    po_oligo f, r, a;             /* forward, reverse and ALT-allele primer, 5'->3'                   */
+    int32_t goodness;             /* score_kasp                                                       */
+    int32_t qbits;                /* PO_Q_* | PO_Q_REF_DIMER | PO_Q_ALT_DIMER                         */
+    uint8_t dir;                  /* 0: the marker primers are forward, 1: reverse                    */
+    uint8_t pad[7];
+} po_kasp_pair;                   /* 64 bytes */
+
+/* markers[n]: templates of ONE common length (<= 512 nt); starts[n]: hroi.start (genome coordinate of
+ * template base 0); maps[n][3][16]: inclusion maps mism, partial_mism, all as bit maps (bit p % 32 of
+ * word p / 32: base p may be covered by a primer); mutations of marker k: entries mut_seg[k] ..
+ * mut_seg[k+1]-1 of mut_pos (genome coordinate) / mut_aaf / mut_indel (ignored without
+ * with_mutations).  `picker`: designPrimers settings, num_return = depth (cli_kasp --depth, 100).
+ * out[n][top_n] / n_out[n]: the selected triples of every marker in report order (descending
+ * goodness, merge order inside a class); n_merged[n] (optional): pairs in the marker's repository. */
+int po_kasp_design_batch(po_ctx *ctx, const po_p3_settings *picker, const po_kasp_design_params *params,
+                         const po_kasp_marker *markers, const int64_t *starts, int64_t n_markers,
+                         const uint32_t *maps, const int64_t *mut_pos, const double *mut_aaf,
+                         const int32_t *mut_indel, const int64_t *mut_seg, po_kasp_pair *out,
+                         int32_t *n_out, int32_t *n_merged);
+
+/* Row a4 alone: the excluded-base bit maps of every search type, excl[n_types][n][16] (bit set: no
+ * primer may cover the base), types in the reference's order (_lib_kasp.py:715-718: mism_mut, mism,
+ * partial_mism_mut, partial_mism, all_mut, all with mutations; mism, partial_mism, all without).
+ * kasp_window != 0 applies the KASP marker-window step with PRIMER_MAX_SIZE = max_size; 0 leaves the
+ * maps as PCR / CAPS / HRM use them. */
+int po_kasp_masks_batch(po_ctx *ctx, const int64_t *starts, int64_t n_markers, int32_t tmpl_len,
+                        const uint32_t *maps, const int64_t *mut_pos, const int64_t *mut_seg,
+                        int32_t with_mutations, int32_t kasp_window, int32_t max_size, uint32_t *excl);
 
 /* ---- instrumentation ------------------------------------------------------ */
 /* Number of kernels this context has launched since po_init. */

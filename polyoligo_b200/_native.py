@@ -68,6 +68,17 @@ class P3Settings(C.Structure):
                 ("n_size_ranges", C.c_int32), ("size_lo", C.c_int32 * 8), ("size_hi", C.c_int32 * 8)]
 
 
+class KaspDesignParams(C.Structure):
+    """po_kasp_design_params"""
+    _fields_ = [("min_size", C.c_int32), ("max_size", C.c_int32), ("top_n", C.c_int32), ("with_mutations", C.c_int32),
+                ("tm_delta", C.c_double), ("valid", ValidParams), ("reporters", C.c_uint32 * 8)]
+
+
+# po_kasp_pair: one selected primer triple of a marker (also sharding.SEL_DTYPE)
+KASP_PAIR_DTYPE = np.dtype([("f", "<u4", (4,)), ("r", "<u4", (4,)), ("a", "<u4", (4,)), ("goodness", "<i4"),
+                            ("qbits", "<i4"), ("dir", "u1"), ("pad", "u1", (7,))])
+assert KASP_PAIR_DTYPE.itemsize == 64
+
 P3_OLIGO_DTYPE = np.dtype([("seq", OLIGO_DTYPE), ("tm", "<f8"), ("gc_percent", "<f8"), ("penalty", "<f8"),
                            ("self_any_th", "<f8"), ("self_end_th", "<f8"), ("hairpin_th", "<f8"),
                            ("start", "<i4"), ("len", "<i4"), ("set", "<i4"), ("flags", "<i4")])
@@ -108,6 +119,11 @@ EXPORTS = {
     "po_p3_design_fixed_batch": (C.c_int, [C.c_void_p, C.POINTER(P3Settings), C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(ValidParams),
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "po_kasp_design_batch": (C.c_int, [C.c_void_p, C.POINTER(P3Settings), C.POINTER(KaspDesignParams), C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "po_kasp_masks_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "po_sync": (C.c_int, [C.c_void_p, C.c_void_p]),
     "po_launch_count": (C.c_int64, [C.c_void_p]),
     "po_thal_item_count": (C.c_int64, [C.c_void_p]),
@@ -387,6 +403,45 @@ class Context:
         out = RankOut(*[res[k].ctypes.data for k in ("goodness", "qbits", "tm", "het_tm", "sel", "n_sel")])
         self._check(load().po_rank_pairs_batch(self._h, C.byref(arg), C.byref(out)), "po_rank_pairs_batch")
         return res
+
+    def kasp_design(self, settings, params, markers, starts, maps_bits, mut_pos=None, mut_aaf=None, mut_indel=None,
+                    mut_seg=None):
+        """po_kasp_design_batch: (records[n, top_n] KASP_PAIR_DTYPE, n_sel[n], n_merged[n])."""
+        markers = np.ascontiguousarray(markers, dtype=KASP_MARKER_DTYPE)
+        n = len(markers)
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        maps_bits = np.ascontiguousarray(maps_bits, dtype=np.uint32).reshape(n, 3, 16)
+        out = np.zeros((n, params.top_n), dtype=KASP_PAIR_DTYPE)
+        n_out = np.zeros(n, dtype=np.int32)
+        n_merged = np.zeros(n, dtype=np.int32)
+        keep = []
+
+        def ptr(a, dtype):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return a.ctypes.data
+        self._check(load().po_kasp_design_batch(
+            self._h, C.byref(settings), C.byref(params), markers.ctypes.data, starts.ctypes.data, n,
+            maps_bits.ctypes.data, ptr(mut_pos, np.int64), ptr(mut_aaf, np.float64), ptr(mut_indel, np.int32),
+            ptr(mut_seg, np.int64), out.ctypes.data, n_out.ctypes.data, n_merged.ctypes.data), "po_kasp_design_batch")
+        return out, n_out, n_merged
+
+    def kasp_masks(self, starts, tmpl_len, maps_bits, mut_pos=None, mut_seg=None, kasp_window=True, max_size=25):
+        """po_kasp_masks_batch: excluded-base bit maps excl[n_types, n, 16] of every search type."""
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        n = len(starts)
+        maps_bits = np.ascontiguousarray(maps_bits, dtype=np.uint32).reshape(n, 3, 16)
+        with_mut = mut_seg is not None
+        excl = np.zeros((6 if with_mut else 3, n, 16), dtype=np.uint32)
+        mp = np.ascontiguousarray(mut_pos, dtype=np.int64) if with_mut else None
+        ms = np.ascontiguousarray(mut_seg, dtype=np.int64) if with_mut else None
+        self._check(load().po_kasp_masks_batch(self._h, starts.ctypes.data, n, int(tmpl_len), maps_bits.ctypes.data,
+                                               mp.ctypes.data if with_mut else None, ms.ctypes.data if with_mut else None,
+                                               1 if with_mut else 0, 1 if kasp_window else 0, int(max_size),
+                                               excl.ctypes.data), "po_kasp_masks_batch")
+        return excl
 
     # ---- "next" rows: HRM product Tm, mutation annotation ---------------------------
     def tm_nn_batch(self, seqs):

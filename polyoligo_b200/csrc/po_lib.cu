@@ -280,6 +280,7 @@ struct po_ctx {
     DevBuf a, b, out, out2, out3, tmv, gcv, props, overflow, hp_cells;
     DevBuf scratch[12];
     DevBuf p3[28];  // primer picking (po_p3.cuh)
+    DevBuf kd[56];  // fused KASP design (po_kasp_design.cuh)
     unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
     // pinned staging for the host entry points
     DevBuf h_in, h_out;
@@ -374,6 +375,8 @@ extern "C" void po_destroy(po_ctx* ctx) {
     for (DevBuf& sb : ctx->scratch)
         if (sb.p) cudaFree(sb.p);
     for (DevBuf& sb : ctx->p3)
+        if (sb.p) cudaFree(sb.p);
+    for (DevBuf& sb : ctx->kd)
         if (sb.p) cudaFree(sb.p);
     if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
@@ -985,3 +988,4 @@ extern "C" int po_annotate_mutations_batch(po_ctx* ctx, const int64_t* mut_pos, 
 }
 
 #include "po_p3.cuh"
+#include "po_kasp_design.cuh"

@@ -623,12 +623,16 @@ struct P3Lists {
 
 // enumerate + sort; leaves the sorted pool in ctx->p3[1] and the device copies of set_off /
 // list_off in ctx->p3[2] / ctx->p3[3]
+// `dev`: tmpl / mask / set_off are DEVICE pointers (copied device to device) and `dev_total_bases`
+// is set_off[n_sets] (the fused KASP design keeps everything resident).
 static int p3_build_lists(po_ctx* ctx, const po_p3_settings* s, const PoConsts& K, const char* tmpl,
-                          const uint8_t* mask, const int64_t* set_off, int64_t n_sets, P3Lists* L) {
+                          const uint8_t* mask, const int64_t* set_off, int64_t n_sets, P3Lists* L, bool dev = false,
+                          long long dev_total_bases = 0) {
     cudaStream_t st = ctx->stream;
     DevBuf* sb = ctx->p3;
     int rc;
-    const long long total_bases = set_off[n_sets];
+    const long long total_bases = dev ? dev_total_bases : set_off[n_sets];
+    const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const size_t nl = (size_t)(2 * n_sets);
     if ((rc = ensure(ctx, sb[2], 8 * (size_t)(n_sets + 1)))) return rc;
     if ((rc = ensure(ctx, sb[3], 8 * (nl + 1)))) return rc;
@@ -637,10 +641,10 @@ static int p3_build_lists(po_ctx* ctx, const po_p3_settings* s, const PoConsts& 
     if ((rc = ensure(ctx, sb[6], 8 * (nl + 1)))) return rc;
     if ((rc = ensure(ctx, sb[7], 8 * (nl + 1)))) return rc;
     if ((rc = ensure(ctx, sb[26], 16 * (size_t)(total_bases > 0 ? total_bases : 1)))) return rc;  // accepted-length masks
-    CK(cudaMemcpyAsync(sb[2].p, set_off, 8 * (size_t)(n_sets + 1), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(sb[2].p, set_off, 8 * (size_t)(n_sets + 1), kind, st));
     if (total_bases > 0) {
-        CK(cudaMemcpyAsync(sb[4].p, tmpl, (size_t)total_bases, cudaMemcpyHostToDevice, st));
-        if (mask) CK(cudaMemcpyAsync(sb[5].p, mask, (size_t)total_bases, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(sb[4].p, tmpl, (size_t)total_bases, kind, st));
+        if (mask) CK(cudaMemcpyAsync(sb[5].p, mask, (size_t)total_bases, kind, st));
     }
     const uint8_t* d_mask = mask ? (const uint8_t*)sb[5].p : nullptr;
     unsigned long long* d_counts = (unsigned long long*)sb[6].p;
@@ -717,31 +721,22 @@ extern "C" int po_p3_candidates_batch(po_ctx* ctx, const po_p3_settings* s, cons
     return PO_OK;
 }
 
-extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, const char* tmpl, const uint8_t* mask,
-                                        const int64_t* set_off, const int32_t* set_target, int64_t n_sets,
-                                        const po_p3_task* tasks, int64_t n_tasks, const po_valid_params* valid,
-                                        po_p3_oligo* fixed_out, po_p3_pair* pairs_out, int32_t* n_pairs_out) {
-    if (!ctx || !set_off || n_sets < 0 || n_tasks < 0 || (n_tasks > 0 && (!tasks || !pairs_out || !n_pairs_out)))
-        return PO_E_INVALID;
-    int rc = p3_check_settings(ctx, s);
-    if (rc) return rc;
-    if (s->n_size_ranges < 1) {
-        ctx->err = "po_p3_design_fixed_batch: PRIMER_PRODUCT_SIZE_RANGE is empty";
-        return PO_E_INVALID;
-    }
-    if (n_tasks == 0) return PO_OK;
-    for (int64_t t = 0; t < n_tasks; ++t)
-        if (tasks[t].set < 0 || tasks[t].set >= n_sets) {
-            ctx->err = "po_p3_design_fixed_batch: task refers to an unknown template";
-            return PO_E_INVALID;
-        }
-    CK(cudaSetDevice(ctx->device));
+// The search itself.  `dev`: tmpl / mask / set_off / tasks are device pointers (dev_total_bases =
+// set_off[n_sets]) and the results stay on the device -- pairs in ctx->p3[24] (n_tasks x num_return
+// po_p3_pair), pair counts in ctx->p3[25], the given primers' records in ctx->p3[10] -- unless the
+// output pointers are given.
+static int p3_design_fixed_impl(po_ctx* ctx, const po_p3_settings* s, const char* tmpl, const uint8_t* mask,
+                                const int64_t* set_off, const int32_t* set_target, int64_t n_sets,
+                                const po_p3_task* tasks, int64_t n_tasks, const po_valid_params* valid,
+                                po_p3_oligo* fixed_out, po_p3_pair* pairs_out, int32_t* n_pairs_out, bool dev,
+                                long long dev_total_bases) {
+    int rc;
     cudaStream_t st = ctx->stream;
     DevBuf* sb = ctx->p3;
     PoConsts K;
     p3_consts(s, ctx->K, &K);
     P3Lists L;
-    if ((rc = p3_build_lists(ctx, s, K, tmpl, mask, set_off, n_sets, &L))) return rc;
+    if ((rc = p3_build_lists(ctx, s, K, tmpl, mask, set_off, n_sets, &L, dev, dev_total_bases))) return rc;
     const size_t nt = (size_t)n_tasks;
     const int rcap = s->num_return + 2 * P3_K;
     const size_t nslot = nt * P3_K;
@@ -778,7 +773,7 @@ extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, co
     const long long* d_list_off = (const long long*)sb[3].p;
     unsigned long long* d_ctr = (unsigned long long*)sb[22].p;
     const int32_t* d_target = nullptr;
-    CK(cudaMemcpyAsync(d_tasks, tasks, sizeof(po_p3_task) * nt, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_tasks, tasks, sizeof(po_p3_task) * nt, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     if (L.total == 0) CK(cudaMemcpyAsync(sb[3].p, L.list_off.data(), 8 * L.list_off.size(), cudaMemcpyHostToDevice, st));
     if (set_target && n_sets > 0) {
         CK(cudaMemcpyAsync(sb[23].p, set_target, 8 * (size_t)n_sets, cudaMemcpyHostToDevice, st));
@@ -899,9 +894,33 @@ extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, co
     ctx->launches++;
     CK(cudaGetLastError());
     if (fixed_out) CK(cudaMemcpyAsync(fixed_out, d_fixed, sizeof(po_p3_oligo) * nt, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(pairs_out, sb[24].p, sizeof(po_p3_pair) * nt * s->num_return, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(n_pairs_out, sb[25].p, 4 * nt, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (pairs_out)
+        CK(cudaMemcpyAsync(pairs_out, sb[24].p, sizeof(po_p3_pair) * nt * s->num_return, cudaMemcpyDeviceToHost, st));
+    if (n_pairs_out) CK(cudaMemcpyAsync(n_pairs_out, sb[25].p, 4 * nt, cudaMemcpyDeviceToHost, st));
+    if (!dev) CK(cudaStreamSynchronize(st));
 #undef P3CK
     return PO_OK;
+}
+
+extern "C" int po_p3_design_fixed_batch(po_ctx* ctx, const po_p3_settings* s, const char* tmpl, const uint8_t* mask,
+                                        const int64_t* set_off, const int32_t* set_target, int64_t n_sets,
+                                        const po_p3_task* tasks, int64_t n_tasks, const po_valid_params* valid,
+                                        po_p3_oligo* fixed_out, po_p3_pair* pairs_out, int32_t* n_pairs_out) {
+    if (!ctx || !set_off || n_sets < 0 || n_tasks < 0 || (n_tasks > 0 && (!tasks || !pairs_out || !n_pairs_out)))
+        return PO_E_INVALID;
+    int rc = p3_check_settings(ctx, s);
+    if (rc) return rc;
+    if (s->n_size_ranges < 1) {
+        ctx->err = "po_p3_design_fixed_batch: PRIMER_PRODUCT_SIZE_RANGE is empty";
+        return PO_E_INVALID;
+    }
+    if (n_tasks == 0) return PO_OK;
+    for (int64_t t = 0; t < n_tasks; ++t)
+        if (tasks[t].set < 0 || tasks[t].set >= n_sets) {
+            ctx->err = "po_p3_design_fixed_batch: task refers to an unknown template";
+            return PO_E_INVALID;
+        }
+    CK(cudaSetDevice(ctx->device));
+    return p3_design_fixed_impl(ctx, s, tmpl, mask, set_off, set_target, n_sets, tasks, n_tasks, valid, fixed_out,
+                                pairs_out, n_pairs_out, false, 0);
 }

@@ -130,6 +130,48 @@ def _slot_geometry(marker_idx, ref_len, alt_len, length, lo, hi):
     return start.astype(np.int32), ln.astype(np.int32)
 
 
+def pack_maps(maps):
+    """The three inclusion maps (n, L) bool -> (n, 3, 16) uint32 bit maps (mism, partial_mism, all): bit p % 32 of
+    word p / 32 set iff a primer may cover base p."""
+    out = []
+    for name in ("mism", "partial_mism", "all"):
+        m = np.asarray(maps[name], dtype=bool)
+        n, length = m.shape
+        full = np.zeros((n, 512), dtype=np.uint8)
+        full[:, :length] = m
+        out.append(np.packbits(full, axis=1, bitorder="little").view("<u4").reshape(n, 16))
+    return np.ascontiguousarray(np.stack(out, axis=1))
+
+
+def design_markers_fused(data, n_primers=10, reporters=None, device=None, ctx=None):
+    """The same design as design_markers_arrays through ONE C call per marker set (po_kasp_design_batch):
+    masks, marker-primer tasks, the round-robin merge, coordinates and the ranking all run on the device;
+    the host packs the inputs and receives the selected triples.  Returns ``(records, n_sel, n_merged)``:
+    records[n, n_primers] of _native.KASP_PAIR_DTYPE in report order (sharding.compact_selection layout)."""
+    g = lib_primer3.PRIMER3_GLOBALS
+    settings = primer3_bindings.settings_from_globals()
+    templates = np.ascontiguousarray(data["templates"], dtype=np.uint8)
+    n = len(templates)
+    params = _native.KaspDesignParams()
+    params.min_size, params.max_size = int(g["PRIMER_MIN_SIZE"]), int(g["PRIMER_MAX_SIZE"])
+    params.top_n = int(n_primers)
+    params.with_mutations = 1 if data.get("mut_seg") is not None else 0
+    params.tm_delta = float(lib_primer3.TM_DELTA)
+    params.valid = lib_primer3.valid_params()
+    rep = _native.pack(list(reporters or ("", "")))
+    for k in range(8):
+        params.reporters[k] = int(rep["w"].reshape(-1)[k])
+    alt_len = np.array([len(a) for a in data["alt"]], dtype=np.int32)
+    del alt_len
+    rec = marker_records(templates, np.asarray(data["marker_idx"], dtype=np.int64),
+                         np.asarray(data["ref_len"], dtype=np.int64), data["alt"])
+    c = ctx if ctx is not None else get_context(device)
+    kw = {}
+    if params.with_mutations:
+        kw = dict(mut_pos=data["mut_pos"], mut_aaf=data["mut_aaf"], mut_indel=data["mut_indel"], mut_seg=data["mut_seg"])
+    return c.kasp_design(settings, params, rec, data["starts"], pack_maps(data["maps"]), **kw)
+
+
 def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk=2048, stats=None, workers=2,
                           ctx=None):
     """Runs the pipeline on a marker set laid out like synth_config5()'s result.  Thresholds come

@@ -175,21 +175,29 @@ def gather_selection(records, n_sel, bounds, dist, device=None):
     return np.concatenate(recs), np.concatenate(cnts)
 
 
-def design_markers_sharded(data, rank, world, dist=None, n_primers=10, device=None, timing=None, **kw):
+def design_markers_sharded(data, rank, world, dist=None, n_primers=10, device=None, timing=None, fused=None, **kw):
     """One rank's share of a marker set under torchrun -- the north_star multi-GPU path: a host-side
     partition of the marker list (contiguous, equally sized ranges: every marker of the synthetic set
     costs about the same) plus a gather of the per-marker results on rank 0.  No data-path collective.
     Returns ``(records, n_sel)`` of ALL markers on rank 0 (``compact_selection`` layout), the local
     share without ``dist``, None on the other ranks.  ``timing`` (dict) receives the shard's own
-    design time in seconds."""
+    design time in seconds.  ``fused`` (default: on, unless a ``ctx`` is injected): one
+    po_kasp_design_batch call per shard instead of the array pipeline's call sequence."""
     import time
     from . import kasp_pipeline
     n = len(data["starts"])
     bounds = partition(np.ones(n), world)
     lo, hi = bounds[rank]
+    if fused is None:
+        fused = kw.get("ctx") is None      # the single-call device path, unless a stand-in context is injected
     t0 = time.perf_counter()
-    local = kasp_pipeline.design_markers_arrays(slice_markers(data, lo, hi), n_primers=n_primers, device=device, **kw)
-    recs, cnt = compact_selection(local, n_primers)
+    if fused:
+        recs, cnt, _ = kasp_pipeline.design_markers_fused(slice_markers(data, lo, hi), n_primers=n_primers,
+                                                          reporters=kw.get("reporters"), device=device)
+    else:
+        local = kasp_pipeline.design_markers_arrays(slice_markers(data, lo, hi), n_primers=n_primers, device=device,
+                                                    **kw)
+        recs, cnt = compact_selection(local, n_primers)
     if timing is not None:
         timing["design_s"] = time.perf_counter() - t0
     if dist is None:

@@ -181,3 +181,72 @@ def test_marker_near_the_chromosome_start(ctx):
     finally:
         p3b.resetP3Globals()
     assert total > 100
+
+
+# ---- a4 on the device and the whole design behind one C call (po_kasp_masks_batch, po_kasp_design_batch) ----
+def _bits_to_idx(words, n):
+    bits = np.unpackbits(np.ascontiguousarray(words, dtype="<u4").view(np.uint8), bitorder="little")
+    return [int(x) for x in np.flatnonzero(bits[:n])]
+
+
+def test_mask_kernel_matches_reference_fixture(ctx):
+    # tests/golden/masks.json is written by the reference's own include_mut_in_included_maps, the KASP
+    # window step and get_sequence_excluded_regions (incl. regions that start 3 / 20 / 26 nt into a chromosome)
+    import json
+    from polyoligo_b200 import kasp_pipeline as kp, lib_utils
+    with open(os.path.join(os.path.dirname(__file__), "golden", "masks.json")) as f:
+        cases = json.load(f)["cases"]
+    n, L = len(cases), cases[0]["n"]
+    maps = {k: np.ones((n, L), dtype=bool) for k in ("mism", "partial_mism", "all")}
+    for k, c in enumerate(cases):
+        maps["mism"][k, c["mism"]] = False
+        maps["partial_mism"][k, c["partial_mism"]] = False
+    starts = np.array([c["start"] for c in cases], dtype=np.int64)
+    seg = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum([len(c["mutation_pos"]) for c in cases], out=seg[1:])
+    pos = np.array([p for c in cases for p in c["mutation_pos"]], dtype=np.int64)
+    names = ["mism_mut", "mism", "partial_mism_mut", "partial_mism", "all_mut", "all"]
+    plain = ctx.kasp_masks(starts, L, kp.pack_maps(maps), pos, seg, kasp_window=False)
+    kaspw = ctx.kasp_masks(starts, L, kp.pack_maps(maps), pos, seg, kasp_window=True, max_size=25)
+    checked = 0
+    for k, c in enumerate(cases):
+        for t, name in enumerate(names):
+            assert _bits_to_idx(plain[t, k], L) == c["excluded_idx_after_mut"][name], (k, name)
+            idx = _bits_to_idx(kaspw[t, k], L)
+            regions = [[int(a), int(b)] for a, b in lib_utils.list_2_ranges(idx)] if idx else []
+            assert regions == c["kasp_excluded_regions"][name], (k, name)
+            checked += len(idx)
+    assert checked > 50
+    three = ctx.kasp_masks(starts, L, kp.pack_maps(maps), kasp_window=False)      # no VCF hook: three types
+    assert np.array_equal(three, plain[1::2])
+
+
+def test_fused_design_call_matches_array_pipeline(ctx):
+    from polyoligo_b200 import kasp_pipeline as kp, sharding
+    from helpers import VIC, FAM
+    n = 300
+    data = kp.synth_config5(n, seed=4242)
+    # a few regions at a chromosome start: part of the masks survives the window step there, so the later
+    # search types ask new questions and the merge has to deduplicate
+    near = np.array([3, 10, 20, 24, 25, 26], dtype=np.int64)
+    shift = np.zeros(n, dtype=np.int64)
+    shift[:len(near)] = data["starts"][:len(near)] - near
+    data["mut_pos"] = data["mut_pos"] - np.repeat(shift, np.diff(data["mut_seg"]))
+    data["starts"] = data["starts"] - shift
+    _kasp_defaults()
+    try:
+        res = kp.design_markers_arrays(data, n_primers=10, reporters=(VIC, FAM), chunk=128)
+        want, want_n = sharding.compact_selection(res, 10)
+        got, got_n, merged = kp.design_markers_fused(data, n_primers=10, reporters=(VIC, FAM))
+        # and without the VCF hook (three search types)
+        data3 = dict(data, mut_seg=None)
+        res3 = kp.design_markers_arrays(data3, n_primers=10, reporters=(VIC, FAM), chunk=128)
+        got3, got3_n, merged3 = kp.design_markers_fused(data3, n_primers=10, reporters=(VIC, FAM))
+    finally:
+        p3b.resetP3Globals()
+    assert np.array_equal(got_n, want_n) and want_n.sum() > 1000
+    assert np.array_equal(merged, np.diff(res["seg"]))
+    assert got.tobytes() == want.tobytes()
+    want3, want3_n = sharding.compact_selection(res3, 10)
+    assert np.array_equal(got3_n, want3_n) and np.array_equal(merged3, np.diff(res3["seg"]))
+    assert got3.tobytes() == want3.tobytes()
