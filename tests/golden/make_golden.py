@@ -431,12 +431,214 @@ def golden_design(rng):
     dump("design.json", {"globals": KASP_GLOBALS, "tm_delta": 5.0, "kasp": kasp_cases, "pcr": pcr_cases})
 
 
+def golden_pcr_main(rng):
+    """_lib_pcr.main (reference :222-356) and _lib_hrm.main (:190-341) from the point where the two
+    homolog-mapped flank ROIs exist: include_mut_in_included_maps, Region.merge_with_primers
+    (lib_markers.py:403-449), get_sequence_excluded_regions, the default product range (:323-324), one
+    design_primers per search mask (picker answers CANNED from the picker oracle), heterodimers,
+    add_mutations, (HRM: PCRproduct.get_hrm_temps,) classify, prune and the report writer -- all the
+    reference's own code on a synthetic genome behind a stand-in BLAST hook (BLAST itself is external)."""
+    import tempfile
+    from oracle import p3_oracle
+    import polyoligo._lib_pcr as lpcr
+    import polyoligo._lib_hrm as lhrm
+    import polyoligo.lib_markers as lm
+    import polyoligo.lib_vcf as lv
+    oracle = Oracle()
+    pcr_globals = dict(PRIMER_OPT_SIZE=20, PRIMER_MIN_SIZE=18, PRIMER_MAX_SIZE=25, PRIMER_OPT_TM=60.0,
+                       PRIMER_MIN_TM=55.0, PRIMER_MAX_TM=65.0, PRIMER_MIN_GC=20.0, PRIMER_MAX_GC=80.0)
+
+    class FakeBlast:                      # lib_blast.BlastDB.fetch: {name: sequence} of 1-based closed ranges
+        def __init__(self, genome):
+            self.genome = genome
+
+        def fetch(self, query):
+            q = query[0]
+            return {"%s:%d-%d" % (q["chr"], q["start"], q["stop"]): self.genome[q["start"] - 1:q["stop"]]}
+
+    def hroi_at(blast, pos, outer, maps_p, muts, marker):
+        lp_, rp_ = lu.get_n_padding(1, outer)
+        h = lm.ROI(chrom="chrG", start=pos - lp_, stop=pos + rp_, blast_hook=blast, vcf_hook=True, name="t", marker=marker)
+        n = h.n
+        mism = rng.random(n) < maps_p[0]
+        partial = mism | (rng.random(n) < maps_p[1])
+        h.p3_sequence_included_maps = {"all": np.repeat(True, n), "partial_mism": partial, "mism": mism}
+        h.mutations = [m for m in muts if h.start <= m.pos <= h.stop]
+        return h
+
+    cases = []
+    specs = [("PCR", 300, 250, False), ("PCR", 90, 250, True), ("PCR", 1200, 250, False), ("HRM", 1, 1000, False),
+             ("HRM", 1, 1000, True), ("CAPS", 1, 400, False), ("CAPS", 1, 400, True)]
+    import polyoligo._lib_caps as lcaps
+    wanted = ["EcoRI", "BamHI", "HindIII", "HpaII", "TaqI", "AluI", "AarI", "XbaI", "PstI", "KpnI", "SmaI", "NotI"]
+    all_enzymes = lcaps.get_enzymes(included_enzymes=None)
+    fragment_min_size = 100            # cli_caps.py --fragment_min_size (flanks and this kept small: the picker oracle is eager)
+    for assay, tlen, outer, narrow in specs:
+        genome = rand_seq(rng, 4000, gc=0.45)
+        ts = int(rng.integers(1200, 1600))
+        if assay == "CAPS":              # the REF allele completes the only EcoRI site of the neighbourhood
+            genome = genome.replace("GAATTC", "GATATC")
+            genome = genome[:ts - 3] + "GAATTC" + genome[ts + 3:]
+        blast = FakeBlast(genome)
+        marker = None
+        if assay in ("HRM", "CAPS"):
+            ref = genome[ts - 1]
+            alt = rng.choice([c for c in "ACGT" if c != ref])
+            marker = types.SimpleNamespace(name="mk", chrom="chrG", pos1=ts, ref=ref, alt=str(alt), n=1)
+        muts = []
+        for pos in np.sort(rng.choice(np.arange(ts - 600, ts + tlen + 600), 70, replace=False)):
+            pos = int(pos)
+            r0 = genome[pos - 1]
+            kind = len(muts) % 9
+            aaf = float(rng.choice([0.02, 0.099, 0.1, 0.3]))
+            if kind == 4:                # deletion of 1-3 bases (VCF style: the anchor base stays)
+                k = int(rng.integers(1, 4))
+                muts.append(lv.Mutation("chrG", pos, genome[pos - 1:pos + k], [r0], aaf=aaf))
+            elif kind == 7:              # insertion, one of them long enough for the 'I' quality flag
+                k = 60 if len(muts) == 7 else int(rng.integers(1, 5))
+                muts.append(lv.Mutation("chrG", pos, r0, [r0 + rand_seq(rng, k)], aaf=aaf))
+            else:
+                alts = [c for c in "ACGT" if c != r0]
+                pick = [alts[int(rng.integers(0, 3))]] if kind != 2 else alts[:2]
+                muts.append(lv.Mutation("chrG", pos, r0, pick, aaf=aaf))
+        region = lm.Region(chrom="chrG", start=ts, stop=ts + tlen - 1, blast_hook=blast, vcf_hook=True, name="reg%d" % len(cases),
+                           marker=marker)
+        if assay in ("HRM", "CAPS"):     # _lib_hrm.main :231-252, _lib_caps.main :253-274: flanks at +- OUTER_LEN / 2
+            lpos, rpos = int(region.start - outer / 2), int(region.start + outer / 2)
+            flank = outer
+        else:                            # _lib_pcr.main :257-278
+            lpos, rpos, flank = region.start, region.stop, outer
+        # narrow: a homolog exists, so "mism" / "partial_mism" keep only the few distinguishing bases
+        # (lib_markers.py:236-243); otherwise no homolog was found and every map is all-True (:232-235)
+        p = (1.0, 1.0) if not narrow else (0.10, 0.15)
+        region.left_roi = hroi_at(blast, lpos, flank, p, muts, marker)
+        region.right_roi = hroi_at(blast, rpos, flank, p, muts, marker)
+        inputs = {side: {"start": h.start, "stop": h.stop,
+                         "maps": {k: [int(x) for x in np.flatnonzero(~v)] for k, v in h.p3_sequence_included_maps.items()},
+                         "mutations": [[m.pos, m.ref, m.alt, m.aaf, int(m.indel_size)] for m in h.mutations]}
+                  for side, h in (("left", region.left_roi), ("right", region.right_roi))}
+        lp.include_mut_in_included_maps(region.left_roi)
+        lp.include_mut_in_included_maps(region.right_roi)
+        if assay == "CAPS":              # _lib_caps.main :298-311: room for the fragments around the marker
+            region = lm.Region(chrom=region.chrom, start=region.marker.pos1 - fragment_min_size,
+                               stop=region.marker.pos1 + fragment_min_size, blast_hook=blast, vcf_hook=True,
+                               name=region.name, marker=marker, left_roi=region.left_roi, right_roi=region.right_roi)
+        target = {"start": region.start, "stop": region.stop}
+        region = region.merge_with_primers()
+        lp.get_sequence_excluded_regions(region)
+        merged = {"start": region.start, "stop": region.stop, "n": region.n, "seq": region.seq,
+                  "target": region.p3_sequence_target,
+                  "excluded_idx": {k: [int(x) for x in np.flatnonzero(~v)] for k, v in region.p3_sequence_included_maps.items()},
+                  "excluded_regions": {k: [[int(a), int(b)] for a, b in v] for k, v in region.p3_sequence_excluded_regions.items()}}
+        # ---- the design loop, picker answers canned ----
+        lp.PRIMER3_GLOBALS.clear()
+        lp.PRIMER3_GLOBALS.update(pcr_globals)
+        if assay == "HRM":
+            lp.PRIMER3_GLOBALS["PRIMER_PRODUCT_SIZE_RANGE"] = [[40, 75], [40, 150]]
+        if assay == "CAPS":              # _lib_caps.main :343 sets it unconditionally
+            lp.PRIMER3_GLOBALS["PRIMER_PRODUCT_SIZE_RANGE"] = [[region.p3_sequence_target[0][1], region.n]]
+        depth = 12
+        lp.PRIMER3_GLOBALS["PRIMER_NUM_RETURN"] = depth
+        lp.set_tm_delta(5.0)
+        if "PRIMER_PRODUCT_SIZE_RANGE" not in lp.PRIMER3_GLOBALS:
+            lp.PRIMER3_GLOBALS["PRIMER_PRODUCT_SIZE_RANGE"] = [[region.p3_sequence_target[0][1], region.n]]
+        size_ranges = tuple(tuple(x) for x in lp.PRIMER3_GLOBALS["PRIMER_PRODUCT_SIZE_RANGE"])
+        so = dict(min_size=18, opt_size=20, max_size=25, num_return=depth, min_tm=55.0, opt_tm=60.0, max_tm=65.0,
+                  min_gc=20.0, max_gc=80.0, size_ranges=size_ranges,
+                  # ThermoAnalysis()'s salt, so that picked primers also pass Primer.is_valid and the
+                  # max_unique / search-order logic has something to select from (answers are canned)
+                  dv_conc=0.0, dntp_conc=0.0)
+        canned = []
+
+        def fake_design(seq_args, so=so, canned=canned):
+            excluded = [tuple(x) for x in seq_args.get("SEQUENCE_EXCLUDED_REGION", [])]
+            tgt = seq_args.get("SEQUENCE_TARGET")
+            res = p3_oracle.design(oracle, so, seq_args["SEQUENCE_TEMPLATE"], excluded=excluded,
+                                   target=tuple(tgt[0]) if tgt else None)
+            d = _p3_dict(res)
+            canned.append({"excluded": [list(x) for x in excluded], "answer": list(d.items())})
+            return d
+
+        sys.modules["primer3"].bindings.designPrimers = fake_design
+        if assay in ("HRM", "CAPS"):
+            pcr = lhrm.PCR(snp_id=marker.name, chrom=marker.chrom, pos=marker.pos1, ref=marker.ref, alt=marker.alt)
+        else:
+            pcr = lp.PCR(chrom=region.chrom, name=region.name)
+        for st in ["mism_mut", "mism", "partial_mism_mut", "partial_mism", "all_mut", "all"]:
+            if len(pcr.pps) < depth:
+                pcr.pps = lpcr.design_primers(pps_repo=pcr.pps, roi=region, sequence_target=region.p3_sequence_target,
+                                              sequence_excluded_region=region.p3_sequence_excluded_regions[st],
+                                              n_primers=depth, max_unique=2)
+        pcr.check_heterodimerization()
+        pcr.add_mutations(region.mutations)
+        hrm_rows = None
+        caps_rows = None
+        enzymes = None
+        repo_all = [_pp_row(pp) for pp in pcr.pps]
+        if assay == "CAPS":              # _lib_caps.main :369-380
+            enzymes = [dict(e) for e in all_enzymes if e["name"] in wanted]
+            fixture_enzymes = [dict(e) for e in enzymes]
+            pruned = []
+            for pp in pcr.pps:
+                prod = lm.PCRproduct(roi=region, pp=pp)
+                prod.will_it_cut(enzymes=enzymes, min_fragment_size=fragment_min_size)
+                if len(prod.enzymes) > 0:
+                    pp.enzymes = prod.enzymes
+                    pp.seq_x = prod.roi.seq_x
+                    pruned.append(pp)
+            pcr.pps = pruned
+            caps_rows = [[e["name"] for e in pp.enzymes] for pp in pcr.pps]
+            pcr.classify(assay_name="CAPS")
+            n_kept = pcr.prune(5)
+        elif assay == "HRM":
+            for pp in pcr.pps:
+                prod = lm.PCRproduct(roi=region, pp=pp)
+                prod.get_hrm_temps()
+                pp.hrm = prod.hrm
+                pp.seq_x = prod.roi.seq_x
+            hrm_rows = [dict(pp.hrm) for pp in pcr.pps]
+            pcr.classify(assay_name="HRM")
+            # PCR.prune orders a goodness class with np.argsort(-delta) "while keeping ties ordered"
+            # (lib_primer3.py:444 and its comment); numpy's default sort is not stable (SIMD quicksort,
+            # the tie order depends on the numpy build and the CPU), so the fixture is written with the
+            # stable sort the comment asks for
+            plain_argsort = np.argsort
+            np.argsort = lambda a, *args, **kw: plain_argsort(a, *args, **{**kw, "kind": "stable"})
+            try:
+                n_kept = pcr.prune(5, assay_name="HRM")
+            finally:
+                np.argsort = plain_argsort
+        else:
+            pcr.classify(assay_name="PCR")
+            n_kept = pcr.prune(5)
+        repo = [_pp_row(pp) for pp in pcr.pps]
+        with tempfile.TemporaryDirectory() as tmp:
+            mod = {"HRM": lhrm, "CAPS": lcaps, "PCR": lpcr}[assay]
+            mod.print_report(pcr, os.path.join(tmp, "rep"))
+            mod.print_report_header(os.path.join(tmp, "hdr.txt"))
+            report = {k: open(os.path.join(tmp, k)).read() for k in ("rep.txt", "rep.bed", "hdr.txt")}
+        cases.append({"assay": assay, "genome": genome, "target": target, "outer": outer, "inputs": inputs,
+                      "marker": None if marker is None else {"name": marker.name, "chrom": marker.chrom,
+                                                              "pos1": marker.pos1, "ref": marker.ref, "alt": marker.alt},
+                      "merged": merged, "size_ranges": [list(x) for x in size_ranges], "depth": depth, "canned": canned,
+                      "repo": repo, "repo_all": repo_all, "hrm": hrm_rows, "caps": caps_rows,
+                      "enzymes": fixture_enzymes if assay == "CAPS" else None,
+                      "fragment_min_size": fragment_min_size if assay == "CAPS" else None, "goodness": [int(pp.goodness) for pp in pcr.pps],
+                      "n_kept": int(n_kept), "report": report,
+                      "mutations": [[m.pos, m.ref, m.alt, m.aaf, int(m.indel_size)] for m in region.mutations]})
+    sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
+    dump("pcr_main.json", {"globals": pcr_globals, "tm_delta": 5.0, "cases": cases})
+
+
 if __name__ == "__main__":
     if "--offtargets-only" in sys.argv:
         golden_offtargets(np.random.default_rng(20240611))
         sys.exit(0)
     if "--design-only" in sys.argv:
         golden_design(np.random.default_rng(20240610))
+        sys.exit(0)
+    if "--pcr-main-only" in sys.argv:
+        golden_pcr_main(np.random.default_rng(20240612))
         sys.exit(0)
     rng = np.random.default_rng(20240608)
     golden_marker_primers(rng)
@@ -447,3 +649,4 @@ if __name__ == "__main__":
     golden_mutations(np.random.default_rng(20240609))
     golden_design(np.random.default_rng(20240610))
     golden_offtargets(np.random.default_rng(20240611))
+    golden_pcr_main(np.random.default_rng(20240612))

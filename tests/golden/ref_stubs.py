@@ -70,6 +70,10 @@ def install(oracle):
 
     seq_utils.GC = GC
     seq_utils.MeltingTemp = types.ModuleType("Bio.SeqUtils.MeltingTemp")
+    from oracle.polyoligo_oracle import tm_nn
+    # Biopython 1.76 MeltingTemp.Tm_NN with default arguments (restated in oracle/polyoligo_oracle.py, pinned
+    # by the value Biopython's documentation prints); the reference calls Tm_NN(seq, strict=False)
+    seq_utils.MeltingTemp.Tm_NN = lambda seq, strict=True, **kw: tm_nn(str(seq))
     bio.Seq = bio_seq
     bio.SeqUtils = seq_utils
     mods = {"primer3": primer3, "primer3.thermoanalysis": ta, "primer3.bindings": bindings, "Bio": bio,
