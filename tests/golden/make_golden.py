@@ -630,12 +630,70 @@ def golden_pcr_main(rng):
     dump("pcr_main.json", {"globals": pcr_globals, "tm_delta": 5.0, "cases": cases})
 
 
+def golden_lib_markers(rng):
+    """lib_markers.Marker (:297-389: '*' alleles, names, parse_indels, assert_marker), ROI sequences
+    (:53-77: seq, seq_alt, seq_x) and ROI.upload_mutations (:279-294) on a synthetic genome."""
+    import pandas as pd
+    import polyoligo.lib_markers as lm
+
+    class FakeBlast:
+        def __init__(self, genome):
+            self.genome = genome
+
+        def fetch(self, query):
+            q = query[0]
+            return {"%s:%d-%d" % (q["chr"], q["start"], q["stop"]): self.genome[q["start"] - 1:q["stop"]]}
+
+    genome = rand_seq(rng, 600, gc=0.5).lower()          # lower case on purpose: ROI upper-cases
+    blast = FakeBlast(genome)
+    cases = []
+    specs = [("m_1", 100, None, "G"), (".", 200, "*", "ACG"), (None, 300, None, "*"), ("x", 301, "AC", "*"),
+             ("snp_b", 50, None, "T"), ("mnp", 120, 3, "TT")]
+    for name, pos, ref, alt in specs:
+        if ref is None:
+            ref = genome[pos].upper()
+        elif isinstance(ref, int):
+            ref = genome[pos:pos + ref].upper()
+        elif ref == "AC":
+            ref = genome[pos:pos + 2].upper()
+        m = lm.Marker(name=name, chrom="chrM", pos=pos, ref_allele=ref, alt_allele=alt)
+        before = dict(name=m.name, pos=m.pos, pos1=m.pos1, ref=m.ref, alt=m.alt, variant=m.variant, n=m.n)
+        err = m.assert_marker(blast)
+        m.parse_indels(blast)
+        after = dict(ref=m.ref, alt=m.alt, variant=m.variant, n=m.n, is_indel=m.is_indel)
+        rois = []
+        for a, b in ((m.pos1 - 20, m.pos1 + 20), (m.pos1, m.pos1), (m.pos1 + 5, m.pos1 + 30)):
+            roi = lm.ROI(chrom="chrM", start=a, stop=b, blast_hook=blast, marker=m)
+            rois.append(dict(start=a, stop=b, name=roi.name, seq=roi.seq, seq_alt=roi.seq_alt, seq_x=roi.seq_x, n=roi.n))
+        cases.append(dict(args=[name, pos, ref, alt], before=before, err=err, after=after, rois=rois))
+    wrong = lm.Marker(name="bad", chrom="chrM", pos=10, ref_allele={"A": "C"}.get(genome[10].upper(), "A"), alt_allele="G")
+    bad_err = wrong.assert_marker(blast)
+
+    class FakeVcf:
+        def fetch_genotypes(self, chrom, start, stop):
+            pos = [p for p in (95, 101, 110, 140) if start <= p <= stop]
+            G = pd.DataFrame({p: [0, 1, 2] for p in pos})
+            return G, [types.SimpleNamespace(pos=p) for p in pos]
+
+    ups = []
+    for mpos in (100, 105):          # marker.pos1 = 101 is among the variants / 106 is not
+        m = lm.Marker(name="u", chrom="chrM", pos=mpos, ref_allele=genome[mpos].upper(), alt_allele="T")
+        roi = lm.ROI(chrom="chrM", start=90, stop=150, blast_hook=blast, vcf_hook=FakeVcf(), marker=m)
+        roi.upload_mutations()
+        ups.append(dict(marker_pos=mpos, mutation_pos=[x.pos for x in roi.mutations], columns=[int(c) for c in roi.G.columns]))
+    dump("lib_markers.json", {"genome": genome, "cases": cases, "bad_args": ["bad", 10, wrong.ref, "G"], "bad_err": bad_err,
+                              "upload": ups})
+
+
 if __name__ == "__main__":
     if "--offtargets-only" in sys.argv:
         golden_offtargets(np.random.default_rng(20240611))
         sys.exit(0)
     if "--design-only" in sys.argv:
         golden_design(np.random.default_rng(20240610))
+        sys.exit(0)
+    if "--lib-markers-only" in sys.argv:
+        golden_lib_markers(np.random.default_rng(20240613))
         sys.exit(0)
     if "--pcr-main-only" in sys.argv:
         golden_pcr_main(np.random.default_rng(20240612))
@@ -650,3 +708,4 @@ if __name__ == "__main__":
     golden_design(np.random.default_rng(20240610))
     golden_offtargets(np.random.default_rng(20240611))
     golden_pcr_main(np.random.default_rng(20240612))
+    golden_lib_markers(np.random.default_rng(20240613))

@@ -218,3 +218,48 @@ def test_flow_with_the_gpu_picker_reproduces_the_reference_reports(assay):
     finally:
         p3b.resetP3Globals()
         lp.PRIMER3_GLOBALS.clear()
+
+
+def test_marker_and_roi_match_reference():
+    # lib_markers.Marker / ROI / upload_mutations against the reference's own objects (host logic)
+    import pandas as pd
+    with open(os.path.join(os.path.dirname(GOLD), "lib_markers.json")) as f:
+        fx = json.load(f)
+    store = lm.SequenceStore({"chrM": fx["genome"]})
+    for case in fx["cases"]:
+        name, pos, ref, alt = case["args"]
+        m = lm.Marker(name=name, chrom="chrM", pos=pos, ref_allele=ref, alt_allele=alt)
+        assert dict(name=m.name, pos=m.pos, pos1=m.pos1, ref=m.ref, alt=m.alt, variant=m.variant, n=m.n) == case["before"]
+        assert m.assert_marker(store) == case["err"]
+        m.parse_indels(store)
+        assert dict(ref=m.ref, alt=m.alt, variant=m.variant, n=m.n, is_indel=m.is_indel) == case["after"]
+        for want in case["rois"]:
+            roi = lm.ROI(chrom="chrM", start=want["start"], stop=want["stop"], blast_hook=store, marker=m)
+            assert dict(start=roi.start, stop=roi.stop, name=roi.name, seq=roi.seq, seq_alt=roi.seq_alt, seq_x=roi.seq_x,
+                        n=roi.n) == want
+    name, pos, ref, alt = fx["bad_args"]
+    assert lm.Marker(name=name, chrom="chrM", pos=pos, ref_allele=ref, alt_allele=alt).assert_marker(store) == fx["bad_err"]
+
+    class Vcf:
+        def fetch_genotypes(self, chrom, start, stop):
+            pos = [p for p in (95, 101, 110, 140) if start <= p <= stop]
+            return pd.DataFrame({p: [0, 1, 2] for p in pos}), [types.SimpleNamespace(pos=p) for p in pos]
+
+    for want in fx["upload"]:
+        mpos = want["marker_pos"]
+        m = lm.Marker(name="u", chrom="chrM", pos=mpos, ref_allele=fx["genome"][mpos].upper(), alt_allele="T")
+        roi = lm.ROI(chrom="chrM", start=90, stop=150, blast_hook=store, vcf_hook=Vcf(), marker=m)
+        roi.upload_mutations()
+        assert [x.pos for x in roi.mutations] == want["mutation_pos"]
+        assert [int(c) for c in roi.G.columns] == want["columns"]
+
+
+def test_get_enzymes_reads_the_reference_format(tmp_path):
+    table = [{"name": "EcoRI", "supplier": "B", "regex": {"F": "GAATTC", "R": "GAATTC"}},
+             {"name": "BsaI", "supplier": "N", "regex": {"F": "GGTCTC", "R": "GAGACC"}}]
+    fn = tmp_path / "type2.json"
+    fn.write_text(json.dumps(table))
+    assert caps.get_enzymes(filename=str(fn)) == table
+    assert [e["name"] for e in caps.get_enzymes(included_enzymes=["BsaI"], filename=str(fn))] == ["BsaI"]
+    with pytest.raises(FileNotFoundError):
+        caps.get_enzymes(filename=str(tmp_path / "absent.json"))
