@@ -228,7 +228,7 @@ def run_config5(args, rank, world, local_rank, barrier, dist, reduce_max):
     tensors; the gather is inside the timed region.  Wall clock per pass, max over ranks."""
     from polyoligo_b200 import kasp_pipeline as kp, sharding
     set_kasp_globals()
-    workers = 1
+    workers = 2      # design_markers_fused's default: blocks of 4096 markers on two host threads / contexts / streams
     kctxs = [kp._worker_context(local_rank, slot) for slot in range(workers)]
     kp.design_markers_fused(kp.synth_config5(min(4096, max(256, args.markers // world)), seed=1), n_primers=10,
                             reporters=DYES, device=local_rank)  # warm-up (allocations)
@@ -267,10 +267,10 @@ def run_config5(args, rank, world, local_rank, barrier, dist, reduce_max):
                         "off-targets (BASELINE config 5 shape), contiguous equal shards over %d rank(s)" %
                         (args.markers, world),
             "scaling": "strong",
-            "timing": "host wall clock of one pass: sharding.design_markers_sharded = input packing + ONE "
-                      "po_kasp_design_batch call per shard (host buffers in, top-10 triples out) + gather of the "
-                      "per-marker results on rank 0 (dist.gather of byte tensors); max over ranks; best of %d passes"
-                      % len(pass_ms),
+            "timing": "host wall clock of one pass: sharding.design_markers_sharded = input packing + one "
+                      "po_kasp_design_batch call per block of 4096 markers, blocks on two host threads / contexts / "
+                      "streams (host buffers in, top-10 triples out) + gather of the per-marker results on rank 0 "
+                      "(dist.gather of byte tensors); max over ranks; best of %d passes" % len(pass_ms),
             "markers_per_s": args.markers / (best * 1e-3), "ms": best, "pass_ms": pass_ms,
             "thal_evaluations_per_s": sum(p[1] for p in per_rank) / (best * 1e-3),
             "thal_evaluations": int(sum(p[1] for p in per_rank)), "gpu_launches": int(sum(p[2] for p in per_rank)),

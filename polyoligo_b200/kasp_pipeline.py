@@ -47,6 +47,7 @@ def _worker_context(device, slot):
             _worker_contexts[key] = ctx
         return ctx
 
+
 CONFIG5_SEED = 20240608
 _LETTERS = np.frombuffer(b"ACGT", dtype=np.uint8)
 _CODE = np.full(256, 255, dtype=np.uint8)
@@ -143,11 +144,14 @@ def pack_maps(maps):
     return np.ascontiguousarray(np.stack(out, axis=1))
 
 
-def design_markers_fused(data, n_primers=10, reporters=None, device=None, ctx=None):
-    """The same design as design_markers_arrays through ONE C call per marker set (po_kasp_design_batch):
-    masks, marker-primer tasks, the round-robin merge, coordinates and the ranking all run on the device;
-    the host packs the inputs and receives the selected triples.  Returns ``(records, n_sel, n_merged)``:
-    records[n, n_primers] of _native.KASP_PAIR_DTYPE in report order (sharding.compact_selection layout)."""
+def design_markers_fused(data, n_primers=10, reporters=None, device=None, ctx=None, workers=2, block=4096):
+    """The same design as design_markers_arrays through ONE C call per block of markers
+    (po_kasp_design_batch): masks, marker-primer tasks, the round-robin merge, coordinates and the
+    ranking all run on the device; the host packs the inputs and receives the selected triples.
+    Blocks go to ``workers`` host threads, each with its own context and stream, so that the tail of
+    one block's picker rounds (few unfinished tasks, host-driven) overlaps another block's kernels.
+    Returns ``(records, n_sel, n_merged)``: records[n, n_primers] of _native.KASP_PAIR_DTYPE in report
+    order (sharding.compact_selection layout)."""
     g = lib_primer3.PRIMER3_GLOBALS
     settings = primer3_bindings.settings_from_globals()
     templates = np.ascontiguousarray(data["templates"], dtype=np.uint8)
@@ -161,15 +165,43 @@ def design_markers_fused(data, n_primers=10, reporters=None, device=None, ctx=No
     rep = _native.pack(list(reporters or ("", "")))
     for k in range(8):
         params.reporters[k] = int(rep["w"].reshape(-1)[k])
-    alt_len = np.array([len(a) for a in data["alt"]], dtype=np.int32)
-    del alt_len
-    rec = marker_records(templates, np.asarray(data["marker_idx"], dtype=np.int64),
-                         np.asarray(data["ref_len"], dtype=np.int64), data["alt"])
-    c = ctx if ctx is not None else get_context(device)
-    kw = {}
+    marker_idx = np.asarray(data["marker_idx"], dtype=np.int64)
+    ref_len = np.asarray(data["ref_len"], dtype=np.int64)
+    starts = np.ascontiguousarray(data["starts"], dtype=np.int64)
+    mut = None
     if params.with_mutations:
-        kw = dict(mut_pos=data["mut_pos"], mut_aaf=data["mut_aaf"], mut_indel=data["mut_indel"], mut_seg=data["mut_seg"])
-    return c.kasp_design(settings, params, rec, data["starts"], pack_maps(data["maps"]), **kw)
+        mut = (np.ascontiguousarray(data["mut_pos"], dtype=np.int64), np.ascontiguousarray(data["mut_aaf"], dtype=np.float64),
+               np.ascontiguousarray(data["mut_indel"], dtype=np.int32), np.ascontiguousarray(data["mut_seg"], dtype=np.int64))
+
+    def call(c, lo, hi):
+        # the block's inputs are packed here, inside the worker: one block's packing overlaps another's kernels
+        rec = marker_records(templates[lo:hi], marker_idx[lo:hi], ref_len[lo:hi], data["alt"][lo:hi])
+        maps_bits = pack_maps({k: m[lo:hi] for k, m in data["maps"].items()})
+        kw = {}
+        if mut is not None:
+            a0, a1 = int(mut[3][lo]), int(mut[3][hi])
+            kw = dict(mut_pos=mut[0][a0:a1], mut_aaf=mut[1][a0:a1], mut_indel=mut[2][a0:a1], mut_seg=mut[3][lo:hi + 1] - a0)
+        return c.kasp_design(settings, params, rec, starts[lo:hi], maps_bits, **kw)
+
+    bounds = [(b0, min(n, b0 + block)) for b0 in range(0, n, block)]
+    workers = 1 if ctx is not None else max(1, min(workers, len(bounds)))
+    if workers == 1:
+        return call(ctx if ctx is not None else get_context(device), 0, n)
+    slots = list(range(workers))
+    slot_lock = threading.Lock()
+
+    def run(b):
+        with slot_lock:
+            slot = slots.pop()
+        try:
+            return call(_worker_context(device, slot), b[0], b[1])
+        finally:
+            with slot_lock:
+                slots.append(slot)
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        parts = list(pool.map(run, bounds))
+    return tuple(np.concatenate([p[k] for p in parts]) for k in range(3))
 
 
 def design_markers_arrays(data, n_primers=10, reporters=None, device=None, chunk=2048, stats=None, workers=2,

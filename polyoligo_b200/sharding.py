@@ -142,37 +142,69 @@ def compact_selection(res, n_primers):
     return out, np.asarray(res["n_sel"], dtype=np.int32)
 
 
+_gather_buffers = {}
+
+
+def _staging(key, shape, pinned, device=None):
+    """Staging tensors of the gather, allocated once per process and shape (pinned host memory and
+    device buffers are expensive to allocate and would otherwise dominate a sub-second shard)."""
+    import torch
+    t = _gather_buffers.get(key + (shape,))
+    if t is None:
+        if device is not None:
+            t = torch.empty(shape, dtype=torch.uint8, device=device)
+        else:
+            t = torch.empty(shape, dtype=torch.uint8)
+            if pinned:
+                t = t.pin_memory()
+        _gather_buffers[key + (shape,)] = t
+    return t
+
+
 def gather_selection(records, n_sel, bounds, dist, device=None):
     """Gather of the per-marker results of all ranks on rank 0, in marker order, as TENSORS (no
     pickling): every rank contributes one byte tensor padded to the largest shard; with the nccl
-    backend the bytes travel device to device (``device``: this rank's cuda device), with gloo they
-    stay on the host.  ``bounds``: [(start, stop), ...] of every rank's shard.
+    backend the bytes travel device to device (``device``: this rank's cuda device) through
+    staging buffers that are kept between calls, with gloo they stay on the host.  ``bounds``:
+    [(start, stop), ...] of every rank's shard.
     Returns (records[n_total, n_primers], n_sel[n_total]) on rank 0, None elsewhere."""
     import torch
     world, rank = dist.get_world_size(), dist.get_rank()
     n_primers = records.shape[1]
     rows = max(e - s for s, e in bounds)
     row_bytes = n_primers * SEL_DTYPE.itemsize + 4
-    buf = np.zeros((rows, row_bytes), dtype=np.uint8)
+    on_gpu = dist.get_backend() == "nccl"
     m = len(n_sel)
+    host_in = _staging(("in",), (rows, row_bytes), on_gpu)
+    buf = host_in.numpy()
     buf[:m, :row_bytes - 4] = records.view(np.uint8).reshape(m, -1)
     buf[:m, row_bytes - 4:] = n_sel.astype("<i4").view(np.uint8).reshape(m, 4)
-    on_gpu = dist.get_backend() == "nccl"
-    t = torch.from_numpy(buf)
+    buf[m:] = 0
     if on_gpu:
-        t = t.pin_memory().to(torch.device("cuda", device if device is not None else torch.cuda.current_device()),
-                              non_blocking=True)
-    bucket = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
-    dist.gather(t, bucket, dst=0)
+        dev = torch.device("cuda", device if device is not None else torch.cuda.current_device())
+        t = _staging(("dev_in",), (rows, row_bytes), False, dev)
+        t.copy_(host_in, non_blocking=True)
+        out = _staging(("dev_out",), (world, rows, row_bytes), False, dev) if rank == 0 else None
+    else:
+        t = host_in
+        out = _staging(("out",), (world, rows, row_bytes), False) if rank == 0 else None
+    dist.gather(t, list(out.unbind(0)) if rank == 0 else None, dst=0)
     if rank != 0:
         return None
-    parts = [b.cpu().numpy() if on_gpu else b.numpy() for b in bucket]
-    recs, cnts = [], []
+    if on_gpu:
+        host_out = _staging(("host_out",), (world, rows, row_bytes), True)
+        host_out.copy_(out)
+        parts = host_out.numpy()
+    else:
+        parts = out.numpy()
+    n_total = bounds[-1][1] - bounds[0][0]
+    recs = np.empty((n_total, n_primers), dtype=SEL_DTYPE)
+    cnts = np.empty(n_total, dtype=np.int32)
     for (s, e), p in zip(bounds, parts):
         k = e - s
-        recs.append(np.ascontiguousarray(p[:k, :row_bytes - 4]).view(SEL_DTYPE).reshape(k, n_primers))
-        cnts.append(np.ascontiguousarray(p[:k, row_bytes - 4:]).view("<i4").reshape(k))
-    return np.concatenate(recs), np.concatenate(cnts)
+        recs[s - bounds[0][0]:e - bounds[0][0]].view(np.uint8).reshape(k, -1)[:] = p[:k, :row_bytes - 4]
+        cnts[s - bounds[0][0]:e - bounds[0][0]].view(np.uint8).reshape(k, 4)[:] = p[:k, row_bytes - 4:]
+    return recs, cnts
 
 
 def design_markers_sharded(data, rank, world, dist=None, n_primers=10, device=None, timing=None, fused=None, **kw):
