@@ -238,6 +238,8 @@ def test_fused_design_call_matches_array_pipeline(ctx):
         res = kp.design_markers_arrays(data, n_primers=10, reporters=(VIC, FAM), chunk=128)
         want, want_n = sharding.compact_selection(res, 10)
         got, got_n, merged = kp.design_markers_fused(data, n_primers=10, reporters=(VIC, FAM))
+        # the same in blocks of 64 markers on three host threads / contexts / streams
+        blk, blk_n, blk_merged = kp.design_markers_fused(data, n_primers=10, reporters=(VIC, FAM), workers=3, block=64)
         # and without the VCF hook (three search types)
         data3 = dict(data, mut_seg=None)
         res3 = kp.design_markers_arrays(data3, n_primers=10, reporters=(VIC, FAM), chunk=128)
@@ -247,6 +249,7 @@ def test_fused_design_call_matches_array_pipeline(ctx):
     assert np.array_equal(got_n, want_n) and want_n.sum() > 1000
     assert np.array_equal(merged, np.diff(res["seg"]))
     assert got.tobytes() == want.tobytes()
+    assert blk.tobytes() == want.tobytes() and np.array_equal(blk_n, want_n) and np.array_equal(blk_merged, merged)
     want3, want3_n = sharding.compact_selection(res3, 10)
     assert np.array_equal(got3_n, want3_n) and np.array_equal(merged3, np.diff(res3["seg"]))
     assert got3.tobytes() == want3.tobytes()
