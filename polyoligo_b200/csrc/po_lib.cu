@@ -284,6 +284,12 @@ struct po_ctx {
     unsigned long long* d_ctr = nullptr;  // [0] work, [1] overflow_n, [2] work2, [4] overflow2_n, [7] relax
     // pinned staging for the host entry points
     DevBuf h_in, h_out;
+    // po_score_pairs_batch: two buffer sets so that the copies of one chunk overlap the kernels of another
+    struct PipeSlot {
+        DevBuf buf[7];  // a, b, het, hairpin_a, hairpin_b, tm_a, tm_b
+        cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+    } pipe[2];
+    cudaStream_t s_in = nullptr, s_out = nullptr;
     int fast_cap = 0;  // 0 = choose by environment / default
 };
 
@@ -380,6 +386,15 @@ extern "C" void po_destroy(po_ctx* ctx) {
         if (sb.p) cudaFree(sb.p);
     if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
     if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
+    for (auto& ps : ctx->pipe) {
+        for (DevBuf& sb : ps.buf)
+            if (sb.p) cudaFree(sb.p);
+        if (ps.in_done) cudaEventDestroy(ps.in_done);
+        if (ps.comp_done) cudaEventDestroy(ps.comp_done);
+        if (ps.out_done) cudaEventDestroy(ps.out_done);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -627,32 +642,64 @@ extern "C" int po_score_pairs_batch(po_ctx* ctx, const po_oligo* a, const po_oli
     if (!ctx || !a || !b || n < 0) return PO_E_INVALID;
     if (n == 0) return PO_OK;
     CK(cudaSetDevice(ctx->device));
-    const int64_t chunk = 1 << 22;  // bounds device scratch to ~0.7 GB
+    // Chunks of 2^20 pairs through two buffer sets: the H2D copy of chunk k+1 (copy-in stream) and the
+    // D2H copy of chunk k-1 (copy-out stream) run while chunk k is scored (context stream).  With pinned
+    // host buffers the copies disappear behind the kernels; pageable buffers still give correct results.
+    const int64_t chunk = 1 << 20;
     const int64_t m0 = n < chunk ? n : chunk;
     int rc;
-    if ((rc = ensure(ctx, ctx->a, sizeof(po_oligo) * (size_t)m0))) return rc;
-    if ((rc = ensure(ctx, ctx->b, sizeof(po_oligo) * (size_t)m0))) return rc;
-    if (het && (rc = ensure(ctx, ctx->out, sizeof(po_thal_out) * (size_t)m0))) return rc;
-    if (hairpin_a && (rc = ensure(ctx, ctx->out2, sizeof(po_thal_out) * (size_t)m0))) return rc;
-    if (hairpin_b && (rc = ensure(ctx, ctx->out3, sizeof(po_thal_out) * (size_t)m0))) return rc;
-    if (tm_a && (rc = ensure(ctx, ctx->tmv, sizeof(double) * (size_t)m0))) return rc;
-    if (tm_b && (rc = ensure(ctx, ctx->gcv, sizeof(double) * (size_t)m0))) return rc;
-    cudaStream_t st = ctx->stream;
-    for (int64_t s = 0; s < n; s += chunk) {
-        const int64_t m = (n - s) < chunk ? (n - s) : chunk;
-        CK(cudaMemcpyAsync(ctx->a.p, a + s, sizeof(po_oligo) * (size_t)m, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->b.p, b + s, sizeof(po_oligo) * (size_t)m, cudaMemcpyHostToDevice, st));
-        if ((rc = po_score_pairs_batch_dev(ctx, ctx->a.p, ctx->b.p, m, het ? ctx->out.p : nullptr,
-                                           hairpin_a ? ctx->out2.p : nullptr, hairpin_b ? ctx->out3.p : nullptr,
-                                           tm_a ? ctx->tmv.p : nullptr, tm_b ? ctx->gcv.p : nullptr, st)))
-            return rc;
-        if (het) CK(cudaMemcpyAsync(het + s, ctx->out.p, sizeof(po_thal_out) * (size_t)m, cudaMemcpyDeviceToHost, st));
-        if (hairpin_a) CK(cudaMemcpyAsync(hairpin_a + s, ctx->out2.p, sizeof(po_thal_out) * (size_t)m, cudaMemcpyDeviceToHost, st));
-        if (hairpin_b) CK(cudaMemcpyAsync(hairpin_b + s, ctx->out3.p, sizeof(po_thal_out) * (size_t)m, cudaMemcpyDeviceToHost, st));
-        if (tm_a) CK(cudaMemcpyAsync(tm_a + s, ctx->tmv.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, st));
-        if (tm_b) CK(cudaMemcpyAsync(tm_b + s, ctx->gcv.p, sizeof(double) * (size_t)m, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+    if (!ctx->s_in) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (auto& ps : ctx->pipe) {
+            CK(cudaEventCreateWithFlags(&ps.in_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ps.comp_done, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ps.out_done, cudaEventDisableTiming));
+        }
     }
+    void* const host_out[5] = {het, hairpin_a, hairpin_b, tm_a, tm_b};
+    const size_t out_size[5] = {sizeof(po_thal_out), sizeof(po_thal_out), sizeof(po_thal_out), sizeof(double), sizeof(double)};
+    const int n_slots = n > chunk ? 2 : 1;
+    for (int sl = 0; sl < n_slots; ++sl) {
+        auto& ps = ctx->pipe[sl];
+        if ((rc = ensure(ctx, ps.buf[0], sizeof(po_oligo) * (size_t)m0))) return rc;
+        if ((rc = ensure(ctx, ps.buf[1], sizeof(po_oligo) * (size_t)m0))) return rc;
+        for (int o = 0; o < 5; ++o)
+            if (host_out[o] && (rc = ensure(ctx, ps.buf[2 + o], out_size[o] * (size_t)m0))) return rc;
+    }
+    // the scratch thal_dev grows on demand, sized up front: no allocation (= device-wide sync) inside the pipeline
+    if ((rc = ensure(ctx, ctx->overflow, 2 * sizeof(long long) * (size_t)m0))) return rc;
+    {
+        const long long hm = m0 < (long long)PO_HAIRPIN_CHUNK ? m0 : (long long)PO_HAIRPIN_CHUNK;
+        if ((hairpin_a || hairpin_b) &&
+            (rc = ensure(ctx, ctx->hp_cells, sizeof(double2) * (size_t)PO_HAIRPIN32_CAP * (size_t)hm)))
+            return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    int64_t k = 0;
+    for (int64_t s = 0; s < n; s += chunk, ++k) {
+        const int64_t m = (n - s) < chunk ? (n - s) : chunk;
+        auto& ps = ctx->pipe[k & 1];
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ps.comp_done, 0));  // the slot's previous chunk has been read
+        CK(cudaMemcpyAsync(ps.buf[0].p, a + s, sizeof(po_oligo) * (size_t)m, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaMemcpyAsync(ps.buf[1].p, b + s, sizeof(po_oligo) * (size_t)m, cudaMemcpyHostToDevice, ctx->s_in));
+        CK(cudaEventRecord(ps.in_done, ctx->s_in));
+        CK(cudaStreamWaitEvent(st, ps.in_done, 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(st, ps.out_done, 0));          // ... and its results have left the slot
+        if ((rc = po_score_pairs_batch_dev(ctx, ps.buf[0].p, ps.buf[1].p, m, het ? ps.buf[2].p : nullptr,
+                                           hairpin_a ? ps.buf[3].p : nullptr, hairpin_b ? ps.buf[4].p : nullptr,
+                                           tm_a ? ps.buf[5].p : nullptr, tm_b ? ps.buf[6].p : nullptr, st)))
+            return rc;
+        CK(cudaEventRecord(ps.comp_done, st));
+        CK(cudaStreamWaitEvent(ctx->s_out, ps.comp_done, 0));
+        for (int o = 0; o < 5; ++o)
+            if (host_out[o])
+                CK(cudaMemcpyAsync((char*)host_out[o] + out_size[o] * (size_t)s, ps.buf[2 + o].p, out_size[o] * (size_t)m,
+                                   cudaMemcpyDeviceToHost, ctx->s_out));
+        CK(cudaEventRecord(ps.out_done, ctx->s_out));
+    }
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(st));
     return PO_OK;
 }
 
