@@ -81,6 +81,8 @@ class Oracle:
 
     def __init__(self, param_dir=None):
         err = C.create_string_buffer(512)
+        if param_dir is None:      # the same default as the product's Context: upstream's tables when named
+            param_dir = os.environ.get("POLYOLIGO_P3_CONFIG") or None
         d = None if param_dir is None else os.fsencode(param_dir)
         self._p = lib().po_oracle_params_load(d, err, 512)
         if not self._p:

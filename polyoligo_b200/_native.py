@@ -186,12 +186,36 @@ def unpack(oligos):
     return [bytes(r[:int(np.argmax(r == 0))]).decode("ascii") for r in raw]
 
 
+class ParityWarning(UserWarning):
+    """thal runs on the embedded literature tables, not on primer3's own primer3_config/ files."""
+
+
+_warned = False
+
+
+def _warn_embedded_tables():
+    """Once per process: thal results on the embedded tables are UNPINNED against primer3 (DESIGN.md
+    section 2; the one published anchor differs by 10 e.u. of dS).  Pass primer3's primer3_config/
+    directory as ``param_dir`` or set POLYOLIGO_P3_CONFIG to reproduce an installed primer3."""
+    global _warned
+    if not _warned:
+        _warned = True
+        import warnings
+        warnings.warn("polyoligo_b200: thal uses the embedded literature parameter tables; hairpin / dimer Tm are "
+                      "not pinned against primer3 -- set POLYOLIGO_P3_CONFIG=<primer3_config dir> (or param_dir) "
+                      "to load upstream's tables", ParityWarning, stacklevel=3)
+
+
 class Context:
     """One CUDA context of the scoring library on one GPU."""
 
     def __init__(self, device=0, param_dir=None):
         lib = load()
         h = C.c_void_p()
+        if param_dir is None:
+            param_dir = os.environ.get("POLYOLIGO_P3_CONFIG") or None    # upstream's primer3_config/ directory
+        if param_dir is None:
+            _warn_embedded_tables()
         d = None if param_dir is None else os.fsencode(param_dir)
         rc = lib.po_init(int(device), d, C.byref(h))
         if rc:
