@@ -84,6 +84,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
     constexpr bool FAST32 = !HAIRPIN && !COUNT && CAP == PO_DIMER32_CAP;
     using Ws = typename ThalWs<CAP, COUNT, HAIRPIN>::type;
     extern __shared__ __align__(16) unsigned char smem[];
+    if (list && *list_n == 0ull) return;  // an overflow tier nobody reached: skip the table staging (block-uniform)
     SmemTables* tb = reinterpret_cast<SmemTables*>(smem);
     SmemExtra* xt = reinterpret_cast<SmemExtra*>(smem + sizeof(SmemTables));
     Ws* wsAll = reinterpret_cast<Ws*>(smem + sizeof(SmemTables) + sizeof(SmemExtra));
