@@ -627,7 +627,17 @@ def golden_pcr_main(rng):
                       "n_kept": int(n_kept), "report": report,
                       "mutations": [[m.pos, m.ref, m.alt, m.aaf, int(m.indel_size)] for m in region.mutations]})
     sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
-    dump("pcr_main.json", {"globals": pcr_globals, "tm_delta": 5.0, "cases": cases})
+    # the report of a region / marker without any pair (the writers' NA line)
+    empty = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for assay, mod in (("PCR", lpcr), ("HRM", lhrm), ("CAPS", lcaps)):
+            if assay == "PCR":
+                pcr = lp.PCR(chrom="chrG", name="nothing")
+            else:
+                pcr = mod.PCR(snp_id="mk0", chrom="chrG", pos=1234, ref="A", alt="")
+            mod.print_report(pcr, os.path.join(tmp, assay))
+            empty[assay] = {k: open(os.path.join(tmp, assay + k)).read() for k in (".txt", ".bed")}
+    dump("pcr_main.json", {"globals": pcr_globals, "tm_delta": 5.0, "cases": cases, "empty_reports": empty})
 
 
 def golden_lib_markers(rng):

@@ -263,3 +263,16 @@ def test_get_enzymes_reads_the_reference_format(tmp_path):
     assert [e["name"] for e in caps.get_enzymes(included_enzymes=["BsaI"], filename=str(fn))] == ["BsaI"]
     with pytest.raises(FileNotFoundError):
         caps.get_enzymes(filename=str(tmp_path / "absent.json"))
+
+
+def test_reports_of_empty_designs_match_reference(tmp_path):
+    # a region / marker for which no pair survives: the writers' NA line (host only)
+    fx = gold()
+    for assay, mod in MODULES.items():
+        if assay == "PCR":
+            p = lp.PCR(chrom="chrG", name="nothing")
+        else:
+            p = mod.PCR(snp_id="mk0", chrom="chrG", pos=1234, ref="A", alt="")
+        mod.print_report(p, str(tmp_path / assay))
+        for ext in (".txt", ".bed"):
+            assert open(str(tmp_path / assay) + ext).read() == fx["empty_reports"][assay][ext], (assay, ext)
