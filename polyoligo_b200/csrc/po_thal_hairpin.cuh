@@ -212,32 +212,35 @@ __device__ __forceinline__ void hairpin_scan(const Grp<G>& g, const TabAddr& A, 
     *bV = bestV;
 }
 
-// upstream END5_1..END5_4 for position i, all four variants at once: lanes
-// 8g..8g+7 serve variant g+1.  Returns the variant's {H_max, S_max} in every
-// lane of its group.
+// upstream END5_1..END5_4 for FOUR consecutive positions i0 .. i0+3 at once: lanes 8b .. 8b+7 serve position
+// i0 + b, inside them lanes 2(v-1), 2(v-1)+1 serve variant v.  A candidate of position i reads the
+// exterior prefix values HEND5 / SEND5 of k <= i - 5 only (the paired base p is at least four below its
+// partner, k = p - 1 or p - 2), so the four positions of a block depend on nothing inside the block
+// and their candidates are evaluated side by side; the caller then runs upstream's max5() selection
+// position by position.  Returns the variant's {H_max, S_max} in both lanes of its pair.
 template <class WS>
-__device__ __noinline__ double2 end5_all(const SmemTables& tb, const WS& ws, int lane, int i,
-                                            double iH, double iS, double RC, double T2) {
-    const int v = (lane >> 3) + 1, sub = lane & 7;
+__device__ __noinline__ double2 end5_block(const SmemTables& tb, const WS& ws, int lane, int i0, int len,
+                                              double iH, double iS, double RC, double T2) {
+    const int i = i0 + (lane >> 3), v = ((lane >> 1) & 3) + 1, sub = lane & 1;
     const uint8_t* s = ws.s1;
+    const bool in = i <= len;
     const int q = (v <= 2) ? i : i - 1;  // paired 3' base
     double bestT = -PO_INF;
     int bestKey = KEY_NONE;
     double2 best = make_double2(PO_INF, -1.0);
-    // uniform trip count over both columns (i and i-1)
-    const int n_i = i >= 5 ? ws.start[i + 1] - ws.start[i] : 0;
-    const int n_im = i >= 6 ? ws.start[i] - ws.start[i - 1] : 0;
-    const int trips = (max(n_i, n_im) + 7) >> 3;
-    const int ks = q >= 5 ? ws.start[q] : 0, ke = q >= 5 ? ws.start[q + 1] : 0;
+    const int ks = (in && q >= 5) ? ws.start[q] : 0, ke = (in && q >= 5) ? ws.start[q + 1] : 0;
+    const int trips = warp_max_int((ke - ks + 1) >> 1);
+    const int ic = in ? i : 2;   // positions past the oligo only keep the lanes company
+    const int bi = s[ic] & 3, bim = s[ic - 1] & 3;
     for (int it = 0; it < trips; ++it) {
-        const int kc0 = ks + sub + 8 * it;
+        const int kc0 = ks + sub + 2 * it;
         bool act = kc0 < ke;
         const int kc = act ? kc0 : 0;
         const int p = CODE_I(ws.code[kc]);
         const int k = (v == 1 || v == 3) ? p - 1 : p - 2;  // the exterior prefix ends at k
         act &= k >= 0;
         const int kk = act ? k : 0;
-        const int bp = s[kk + 1] & 3, bp2 = s[kk + 2] & 3, bi = s[i] & 3, bim = s[i - 1] & 3;
+        const int bp = s[kk + 1] & 3, bp2 = s[kk + 2] & 3;
         double2 x = make_double2(0.0, 0.0);
         if (v == 2) x = tb.dangle5[(bi * 4 + bp2) * 4 + bp];            // Hd5(i, k+2)
         else if (v == 3) x = tb.dangle3[(bim * 4 + bi) * 4 + bp];       // Hd3(i-1, k+1)
@@ -277,17 +280,12 @@ __device__ __noinline__ double2 end5_all(const SmemTables& tb, const WS& ws, int
             best = make_double2(H, S);
         }
     }
-    // arg-max inside each 8-lane group
-#pragma unroll
-    for (int m = 4; m >= 1; m >>= 1) {
-        const double ot = __shfl_xor_sync(FULL, bestT, m);
-        const int ok = __shfl_xor_sync(FULL, bestKey, m);
-        const double oh = __shfl_xor_sync(FULL, best.x, m), os = __shfl_xor_sync(FULL, best.y, m);
-        if ((ot > bestT) | ((ot == bestT) & (ok < bestKey))) {
-            bestT = ot;
-            bestKey = ok;
-            best = make_double2(oh, os);
-        }
+    // arg-max inside each pair of lanes
+    {
+        const double ot = __shfl_xor_sync(FULL, bestT, 1);
+        const int ok = __shfl_xor_sync(FULL, bestKey, 1);
+        const double oh = __shfl_xor_sync(FULL, best.x, 1), os = __shfl_xor_sync(FULL, best.y, 1);
+        if ((ot > bestT) | ((ot == bestT) & (ok < bestKey))) best = make_double2(oh, os);
     }
     return best;
 }
@@ -311,42 +309,56 @@ __device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtr
         ws.end5t[0] = ws.end5t[1] = po_div(PO_INF + iH, -1.0 + iS + RC);
     }
     __syncwarp();
-    for (int i = 2; i <= len; ++i) {
-        const double hp = ws.end5[0][i - 1], sp = ws.end5[1][i - 1];
-        double hn = hp, sn = sp;
-        double tn = ws.end5t[i - 1];  // T of (hn, sn): the previous quotient, or the chosen variant's
-        // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
-        // upstream's max5() falls through to its last case, which keeps the previous value
-        const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
-        if (any) {
-            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC, T2e);
-            const double T1 = ws.end5t[i - 1];
-            const double Tv = po_div_rej(e.x + iH, e.y + iS + RC);  // {inf, -1}, or dH <= 0 and dS <= 0
-            const double T2 = gw.shfl(Tv, 0), T3 = gw.shfl(Tv, 8), T4 = gw.shfl(Tv, 16), T5 = gw.shfl(Tv, 24);
-            int mx;
-            if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
-            else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
-            else if (T3 > T4 && T3 > T5) mx = 3;
-            else if (T4 > T5) mx = 4;
-            else mx = 5;
-            if (mx > 1) {
-                const double eh = gw.shfl(e.x, (mx - 2) * 8), es = gw.shfl(e.y, (mx - 2) * 8);
-                const double et = mx == 2 ? T2 : mx == 3 ? T3 : mx == 4 ? T4 : T5;
-                const double Gv = eh - (K.temp_k * es);
-                if (Gv < 0.0) {
-                    hn = eh;
-                    sn = es;
-                    tn = et;
+    {
+        double hn = ws.end5[0][1], sn = ws.end5[1][1];
+        double tn = ws.end5t[1];  // T of (hn, sn): the previous quotient, or the chosen variant's
+        for (int i0 = 2; i0 <= len; i0 += 4) {
+            // no finite cell in columns i0-1 .. i0+3: every END5 variant of the block is {inf,-1}
+            const int cfirst = max(i0 - 1, 5), clast = min(i0 + 3, len);
+            const bool any_blk = clast >= cfirst && ws.start[clast + 1] > ws.start[cfirst];
+            double2 e = make_double2(PO_INF, -1.0);
+            double Tv = -PO_INF;
+            if (any_blk) {
+                e = end5_block(tb, ws, lane, i0, len, iH, iS, RC, T2e);
+                Tv = po_div_rej(e.x + iH, e.y + iS + RC);  // {inf, -1}, or dH <= 0 and dS <= 0
+            }
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+                const int i = i0 + b;
+                if (i > len) break;
+                // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
+                // upstream's max5() falls through to its last case, which keeps the previous value
+                const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
+                if (any) {
+                    const double T1 = tn;
+                    const double T2 = gw.shfl(Tv, 8 * b), T3 = gw.shfl(Tv, 8 * b + 2), T4 = gw.shfl(Tv, 8 * b + 4),
+                                 T5 = gw.shfl(Tv, 8 * b + 6);
+                    int mx;
+                    if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
+                    else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
+                    else if (T3 > T4 && T3 > T5) mx = 3;
+                    else if (T4 > T5) mx = 4;
+                    else mx = 5;
+                    if (mx > 1) {
+                        const double eh = gw.shfl(e.x, 8 * b + (mx - 2) * 2), es = gw.shfl(e.y, 8 * b + (mx - 2) * 2);
+                        const double et = mx == 2 ? T2 : mx == 3 ? T3 : mx == 4 ? T4 : T5;
+                        const double Gv = eh - (K.temp_k * es);
+                        if (Gv < 0.0) {
+                            hn = eh;
+                            sn = es;
+                            tn = et;
+                        }
+                    }
+                }
+                if (COUNT) cnt += (lane == 0) ? 4 : 0;
+                if (lane == 0) {
+                    ws.end5[0][i] = hn;
+                    ws.end5[1][i] = sn;
+                    ws.end5t[i] = tn;
                 }
             }
+            __syncwarp();
         }
-        if (COUNT) cnt += (lane == 0) ? 4 : 0;
-        if (lane == 0) {
-            ws.end5[0][i] = hn;
-            ws.end5[1][i] = sn;
-            ws.end5t[i] = tn;
-        }
-        __syncwarp();
     }
     if (COUNT && relax) {
         __syncwarp();
@@ -375,11 +387,12 @@ __device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtr
             // exterior loop: find the structure that ends at or before i
             while (i > 0 && eq5(ws.end5[1][i], ws.end5[1][i - 1]) && eq5(ws.end5[0][i], ws.end5[0][i - 1])) --i;
             if (i == 0) continue;
-            const double2 e = end5_all(tb, ws, lane, i, iH, iS, RC, T2e);
+            // the block form evaluated for position i alone: its four variants sit in lanes 0, 2, 4, 6
+            const double2 e = end5_block(tb, ws, lane, i, len, iH, iS, RC, T2e);
             const double hi_ = ws.end5[0][i], si_ = ws.end5[1][i];
-            const unsigned match = __ballot_sync(FULL, (lane & 7) == 0 && eq5(si_, e.y) && eq5(hi_, e.x));
+            const unsigned match = __ballot_sync(FULL, lane < 8 && (lane & 1) == 0 && eq5(si_, e.y) && eq5(hi_, e.x));
             if (!match) continue;
-            const int v = (__ffs(match) - 1) / 8 + 1;  // upstream's else-if chain: first matching variant only
+            const int v = (__ffs(match) - 1) / 2 + 1;  // upstream's else-if chain: first matching variant only
             const uint8_t* s = ws.s1;
             const int q = (v <= 2) ? i : i - 1;
             int myKey = KEY_NONE;
