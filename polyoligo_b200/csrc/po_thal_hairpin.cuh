@@ -316,39 +316,44 @@ __device__ __noinline__ void hairpin_finish(const SmemTables& tb, const SmemExtr
             // no finite cell in columns i0-1 .. i0+3: every END5 variant of the block is {inf,-1}
             const int cfirst = max(i0 - 1, 5), clast = min(i0 + 3, len);
             const bool any_blk = clast >= cfirst && ws.start[clast + 1] > ws.start[cfirst];
-            double2 e = make_double2(PO_INF, -1.0);
-            double Tv = -PO_INF;
+            // Per position (lanes 8b .. 8b+7 hold position i0 + b): the variant upstream's max5() would take
+            // if the carried value does not beat all four, its values, and whether it is accepted (dG < 0).
+            // None of this depends on the carried value, so the four positions are prepared side by side;
+            // the carry (T1 = the previous position's quotient) is then resolved position by position.
+            double Tmax4 = -PO_INF, et = -PO_INF, eh = PO_INF, es = -1.0;
+            bool take = false;
             if (any_blk) {
-                e = end5_block(tb, ws, lane, i0, len, iH, iS, RC, T2e);
-                Tv = po_div_rej(e.x + iH, e.y + iS + RC);  // {inf, -1}, or dH <= 0 and dS <= 0
+                const double2 e = end5_block(tb, ws, lane, i0, len, iH, iS, RC, T2e);
+                const double Tv = po_div_rej(e.x + iH, e.y + iS + RC);  // {inf, -1}, or dH <= 0 and dS <= 0
+                const double T2 = __shfl_sync(FULL, Tv, 0, 8), T3 = __shfl_sync(FULL, Tv, 2, 8),
+                             T4 = __shfl_sync(FULL, Tv, 4, 8), T5 = __shfl_sync(FULL, Tv, 6, 8);
+                int mx;
+                if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
+                else if (T3 > T4 && T3 > T5) mx = 3;
+                else if (T4 > T5) mx = 4;
+                else mx = 5;
+                eh = __shfl_sync(FULL, e.x, (mx - 2) * 2, 8);
+                es = __shfl_sync(FULL, e.y, (mx - 2) * 2, 8);
+                et = mx == 2 ? T2 : mx == 3 ? T3 : mx == 4 ? T4 : T5;
+                Tmax4 = fmax(fmax(T2, T3), fmax(T4, T5));   // quotients or -inf, never NaN
+                const int i = i0 + (lane >> 3);
+                // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
+                // upstream's max5() falls through to its last case, which keeps the previous value
+                const bool any = i <= len && ((i >= 5 && ws.start[i + 1] > ws.start[i]) ||
+                                              (i >= 6 && ws.start[i] > ws.start[i - 1]));
+                take = any && (eh - (K.temp_k * es)) < 0.0;
             }
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
                 const int i = i0 + b;
                 if (i > len) break;
-                // no finite cell in columns i and i-1: every END5 variant is {inf,-1}, T = -inf, and
-                // upstream's max5() falls through to its last case, which keeps the previous value
-                const bool any = (i >= 5 && ws.start[i + 1] > ws.start[i]) || (i >= 6 && ws.start[i] > ws.start[i - 1]);
-                if (any) {
-                    const double T1 = tn;
-                    const double T2 = gw.shfl(Tv, 8 * b), T3 = gw.shfl(Tv, 8 * b + 2), T4 = gw.shfl(Tv, 8 * b + 4),
-                                 T5 = gw.shfl(Tv, 8 * b + 6);
-                    int mx;
-                    if (T1 > T2 && T1 > T3 && T1 > T4 && T1 > T5) mx = 1;
-                    else if (T2 > T3 && T2 > T4 && T2 > T5) mx = 2;
-                    else if (T3 > T4 && T3 > T5) mx = 3;
-                    else if (T4 > T5) mx = 4;
-                    else mx = 5;
-                    if (mx > 1) {
-                        const double eh = gw.shfl(e.x, 8 * b + (mx - 2) * 2), es = gw.shfl(e.y, 8 * b + (mx - 2) * 2);
-                        const double et = mx == 2 ? T2 : mx == 3 ? T3 : mx == 4 ? T4 : T5;
-                        const double Gv = eh - (K.temp_k * es);
-                        if (Gv < 0.0) {
-                            hn = eh;
-                            sn = es;
-                            tn = et;
-                        }
-                    }
+                if (any_blk) {
+                    // lanes of position b decide with the carried quotient; everybody receives the result
+                    const bool d = take && !(tn > Tmax4);
+                    const double nh = d ? eh : hn, ns = d ? es : sn, nt = d ? et : tn;
+                    hn = gw.shfl(nh, 8 * b);
+                    sn = gw.shfl(ns, 8 * b);
+                    tn = gw.shfl(nt, 8 * b);
                 }
                 if (COUNT) cnt += (lane == 0) ? 4 : 0;
                 if (lane == 0) {
