@@ -59,10 +59,10 @@ __device__ __forceinline__ double2 bonus_lookup(const int32_t* keys, const doubl
     return make_double2(0.0, 0.0);
 }
 
-// upstream calc_hairpin() without its final dG comparison: the hairpin-loop
-// closure value of (i,j); `cur` is the current DP value of the cell.
-__device__ __noinline__ double2 hairpin_closure(const SmemTables& tb, const SmemExtra& X, const PoTables* gt,
-                                                   const uint8_t* s, int i, int j, double2 cur) {
+// The sequence-only part of upstream calc_hairpin(): loop entropy / enthalpy, terminal mismatch or AT
+// penalty, tri- / tetraloop bonus of the hairpin loop closed by (i,j).
+__device__ __noinline__ double2 hairpin_closure_static(const SmemTables& tb, const SmemExtra& X, const PoTables* gt,
+                                                          const uint8_t* s, int i, int j) {
     const int loopSize = j - i - 1;
     double H, S;
     const int li = loopSize <= 30 ? loopSize - 1 : 29;
@@ -108,11 +108,20 @@ __device__ __noinline__ double2 hairpin_closure(const SmemTables& tb, const Smem
         H = PO_INF;
         S = -1.0;
     }
-    if (H > 0 && S > 0 && (!(cur.x > 0) || !(cur.y > 0))) {
-        H = PO_INF;
-        S = -1.0;
-    }
     return make_double2(H, S);
+}
+
+// the part of calc_hairpin() that looks at the cell's current value
+__device__ __forceinline__ double2 hairpin_closure_vs(double2 c, double2 cur) {
+    if (c.x > 0 && c.y > 0 && (!(cur.x > 0) || !(cur.y > 0))) c = make_double2(PO_INF, -1.0);
+    return c;
+}
+
+// upstream calc_hairpin() without its final dG comparison: the hairpin-loop
+// closure value of (i,j); `cur` is the current DP value of the cell.
+__device__ __forceinline__ double2 hairpin_closure(const SmemTables& tb, const SmemExtra& X, const PoTables* gt,
+                                                   const uint8_t* s, int i, int j, double2 cur) {
+    return hairpin_closure_vs(hairpin_closure_static(tb, X, gt, s, i, j), cur);
 }
 
 // index of finite cell (i,j) in the list; caller guarantees it is finite

@@ -244,6 +244,16 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
     }
     __syncwarp();
 
+    // The hairpin-loop closure of every cell (sequence only), 32 cells at a time; it waits in the cell's
+    // own slot, which nothing reads before the cell's column is reached.
+    for (int k0 = 0; k0 < ncell; k0 += 32) {
+        const int k = min(k0 + lane, ncell - 1);
+        const uint32_t code = ws.code[k];
+        const double2 c = hairpin_closure_static(tb, X, gt, ws.s1, CODE_I(code), CODE_J(code));
+        if (k0 + lane < ncell) ws.cell[k] = c;
+    }
+    __syncwarp();
+
     // maxTM2's empty-structure quotient (0 + iH) / (MIN_ENTROPY + iS + RC): the same for every cell
     const double T0_const = po_div(0.0 + iH, PO_MIN_ENTROPY + iS + RC);
     // ---- fillMatrix2 -----------------------------------------------------------
@@ -256,9 +266,11 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
         const uint32_t cmj1 = HP32_COLM(ws, j - 1);
         const uint32_t cmj2 = j >= 7 ? HP32_COLM(ws, j - 2) : 0u;
         // One lane per cell of the column (<= 28): maxTM2 (stack on (i+1, j-1)), candidate-set descriptor
+        double2 closure;   // the cell's loop closure, parked in its slot by the prologue; used in phase C
         {
             const bool act = cs + lane < ce;
             const int k = act ? cs + lane : ce - 1;
+            closure = ws.cell[k];
             const int i = CODE_I(ws.code[k]);
             const int bi = ws.s1[i], bin = ws.s1[i + 1], bjm = ws.s1[j - 1];
             const double S0 = PO_MIN_ENTROPY, H0 = 0.0;
@@ -395,7 +407,7 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
             const int k = act ? cs + lane : ce - 1;
             const int i = CODE_I(ws.code[k]);
             const double2 cur = ws.cell[k];
-            double2 v = hairpin_closure(tb, X, gt, ws.s1, i, j, cur);
+            double2 v = hairpin_closure_vs(closure, cur);
             const double2 sh = rshT[END_IDX(ws.s1[i], ws.s1[i + 1], ws.s1[j + 1])];
             const double G1 = v.x + sh.x - PO_TEMP_KELVIN * (v.y + sh.y);
             const double G2 = cur.x + sh.x - PO_TEMP_KELVIN * (cur.y + sh.y);
