@@ -280,7 +280,11 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
             const double2 st = tb.stack[quad(bi, bin, bj, bjm)];
             double S1 = pv.y + st.y;
             double H1 = pv.x + st.x;
-            const double T1 = po_div(H1 + iH, S1 + iS + RC);
+            // H1 is finite, or +inf without a stackable predecessor: +inf over the (finite) denominator
+            const double den1 = S1 + iS + RC;
+            const bool f1 = fin(H1);
+            const double q1 = po_div_nr(f1 ? H1 + iH : 1.0, den1);
+            const double T1 = f1 ? q1 : (den1 < 0.0 ? -PO_INF : PO_INF);
             if (S1 < PO_MIN_ENTROPY_CUTOFF) {
                 S1 = PO_MIN_ENTROPY;
                 H1 = 0.0;
