@@ -45,6 +45,8 @@ struct Hairpin32Ws {
     uint16_t rowge[36];   // number of byrow entries with row >= r
     typename std::conditional<(CAP <= 256), uint8_t, uint16_t>::type rowmajor[CAP];  // every finite cell, row-major
     uint8_t s1[40];
+    uint2 dpre[CAP];      // per cell: the sequence-only part of its candidate-set descriptor (fill kernel)
+    uint32_t capcol[36];  // interior-capable cells of column c (bit i-1)
 };
 
 // rows i <= j-4 of column j that pair with base j (bit i-1)
@@ -59,15 +61,9 @@ __device__ __forceinline__ int popc_from32(uint32_t m, int x) {  // set bits at 
 // merges column c (final since column c+1 was relaxed) into ws.byrow; returns the new length
 template <int CAP>
 __device__ __forceinline__ int byrow32_merge_col(const SmemTables& tb, Hairpin32Ws<CAP>& ws, int c, int n_by, int lane) {
-    const int bc = ws.s1[c], bcn = ws.s1[c + 1] & 3;
     const uint32_t cm = HP32_COLM(ws, c);
-    // interior-capable cells of the column: tstack[s[c]][s[c+1]][s[i]][s[i-1]] finite (the sentinel
-    // before the first base reads as base 0, exactly like the tq field of the cell codes)
-    uint32_t capm = 0u;
-#pragma unroll
-    for (int nb = 0; nb < 4; ++nb)
-        if (fin(tb.tstack[quad(bc, bcn, 3 - bc, nb)].x)) capm |= (ws.m32[nb] << 1) | (nb == 0 ? 1u : 0u);
-    const uint32_t newm = cm & capm;
+    // interior-capable cells of the column (tabulated per column by the prologue)
+    const uint32_t newm = ws.capcol[c];
     if (newm == 0u) return n_by;  // warp-uniform
     // existing entries move up by the number of new cells in higher rows; chunks from the top down
     for (int base = ((n_by - 1) >> 5) << 5; base >= 0; base -= 32) {
@@ -254,6 +250,59 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
     }
     __syncwarp();
 
+    {
+        // interior-capable cells of every column: tstack[s[c]][s[c+1]][s[i]][s[i-1]] finite (the sentinel
+        // before the first base reads as base 0, exactly like the tq field of the cell codes)
+        const int c = lane + 1;
+        uint32_t cap = 0u;
+        if (c >= 5 && c <= len) {
+            const int bc = ws.s1[c], bcn = ws.s1[c + 1] & 3;
+            uint32_t capm = 0u;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb)
+                if (fin(tb.tstack[quad(bc, bcn, 3 - bc, nb)].x)) capm |= (ws.m32[nb] << 1) | (nb == 0 ? 1u : 0u);
+            cap = HP32_COLM(ws, c) & capm;
+        }
+        ws.capcol[c] = cap;
+        if (lane < 4) ws.capcol[(lane == 0) ? 0 : 32 + lane] = 0u;
+    }
+    // The sequence-only part of every cell's candidate-set descriptor, 32 cells at a time (the per-column
+    // pass runs with 3-4 lanes busy): bulge ranges, the 1x1 cell, table indices.  The interior-loop count
+    // depends on the merge state of the candidate list and stays in the column pass.
+    for (int k0 = 0; k0 < ncell; k0 += 32) {
+        const int k = min(k0 + lane, ncell - 1);
+        const uint32_t code = ws.code[k];
+        const int i = CODE_I(code), j = CODE_J(code);
+        uint2 pk = make_uint2(0u, 0u);
+        if (j - i >= 7) {
+            const int bi = ws.s1[i], bin = ws.s1[i + 1], bj = ws.s1[j], bjm = ws.s1[j - 1];
+            const uint32_t cmj1 = HP32_COLM(ws, j - 1);
+            const uint32_t cmj2 = j >= 7 ? HP32_COLM(ws, j - 2) : 0u;
+            const int q = quad(bi, bin & 3, bj, bjm & 3);
+            const double2 y0 = tb.tstack[q], y3 = tb.stackint2[q];
+            // 1x1 loop: cell (i+2, j-2)
+            const bool star_fin = (j - i >= 8) && ((cmj2 >> (i + 1)) & 1u);
+            const int kstar = star_fin ? ws.start[j - 2] + popc_from32(cmj2, i + 2) : 0;
+            const bool star_cap = star_fin && (ws.code[kstar] & CODE_CAP_BIT);
+            // bulges: column j-1, rows i+2 .. min(j-5, i+1+max_loop) (descending in the list);
+            //         row i+1, columns max(i+5, j-1-max_loop) .. j-2
+            const int hiA = min(j - 5, i + 1 + max_loop);
+            const int aboveA = popc_from32(cmj1, max(hiA, 0));
+            const int nA = max(popc_from32(cmj1, i + 1) - aboveA, 0);
+            const uint32_t rm = HP32_ROWM(ws, i + 1);
+            const int loB = max(i + 5, j - 1 - max_loop);
+            const int belowB = popc_below32(rm, loB - 1);
+            const int nB = max(popc_below32(rm, j - 2) - belowB, 0);
+            const int nS = (star_fin && fin(y3.x) && max_loop >= 2) ? 1 : 0;
+            const unsigned flags = (fin(y0.x) ? 1u : 0u) | (star_cap ? 2u : 0u);
+            pk.x = (unsigned)(nA + nB + nS) | ((unsigned)nA << 8) | ((unsigned)nB << 16) | (flags << 24);
+            pk.y = (unsigned)(ws.start[j - 1] + aboveA) | ((unsigned)(ws.rstart[i + 1] + belowB) << 8) |
+                   ((unsigned)kstar << 16) | ((unsigned)q << 24);
+        }
+        if (k0 + lane < ncell) ws.dpre[k] = pk;
+    }
+    __syncwarp();
+
     // maxTM2's empty-structure quotient (0 + iH) / (MIN_ENTROPY + iS + RC): the same for every cell
     const double T0_const = po_div(0.0 + iH, PO_MIN_ENTROPY + iS + RC);
     // ---- fillMatrix2 -----------------------------------------------------------
@@ -296,33 +345,18 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
             d.i = (uint8_t)i;
             d.Tcur = 0.0;
             if (j - i >= 7) {
-                const int q = quad(bi, bin & 3, bj, bjm & 3);
-                const double2 y0 = tb.tstack[q], y3 = tb.stackint2[q];
-                // 1x1 loop: cell (i+2, j-2)
-                const bool star_fin = (j - i >= 8) && ((cmj2 >> (i + 1)) & 1u);
-                const int kstar = star_fin ? ws.start[j - 2] + popc_from32(cmj2, i + 2) : 0;
-                const bool star_cap = star_fin && (ws.code[kstar] & CODE_CAP_BIT);
+                const uint2 pk = ws.dpre[k];
+                const unsigned flags = pk.x >> 24;
                 // interior loops: byrow prefix of rows >= i+2, minus the 1x1 cell (its last entry)
-                const int n_fast = fin(y0.x) ? (int)ws.rowge[i + 2] - (star_cap ? 1 : 0) : 0;
-                // bulges: column j-1, rows i+2 .. min(j-5, i+1+max_loop) (descending in the list);
-                //         row i+1, columns max(i+5, j-1-max_loop) .. j-2
-                const int hiA = min(j - 5, i + 1 + max_loop);
-                const int aboveA = popc_from32(cmj1, max(hiA, 0));
-                const int nA = max(popc_from32(cmj1, i + 1) - aboveA, 0);
-                const uint32_t rm = HP32_ROWM(ws, i + 1);
-                const int loB = max(i + 5, j - 1 - max_loop);
-                const int belowB = popc_below32(rm, loB - 1);
-                const int nB = max(popc_below32(rm, j - 2) - belowB, 0);
-                const int nS = (star_fin && fin(y3.x) && max_loop >= 2) ? 1 : 0;
+                d.n_fast = (uint16_t)((flags & 1u) ? (int)ws.rowge[i + 2] - (int)((flags >> 1) & 1u) : 0);
+                d.total = (uint16_t)(pk.x & 255u);
+                d.nA = (uint16_t)((pk.x >> 8) & 255u);
+                d.nB = (uint16_t)((pk.x >> 16) & 255u);
+                d.kA0 = (uint16_t)(pk.y & 255u);
+                d.kB0 = (uint16_t)((pk.y >> 8) & 255u);
+                d.kstar = (uint16_t)((pk.y >> 16) & 255u);
+                d.q = (uint8_t)(pk.y >> 24);
                 d.Tcur = po_div_nr(v.x + iH, (v.y + iS) + RC);
-                d.n_fast = (uint16_t)n_fast;
-                d.total = (uint16_t)(nA + nB + nS);
-                d.nA = (uint16_t)nA;
-                d.nB = (uint16_t)nB;
-                d.kA0 = (uint16_t)(ws.start[j - 1] + aboveA);
-                d.kB0 = (uint16_t)(ws.rstart[i + 1] + belowB);
-                d.kstar = (uint16_t)kstar;
-                d.q = (uint8_t)q;
             }
             if (act) {
                 ws.cell[k] = v;
