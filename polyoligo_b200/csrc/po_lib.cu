@@ -60,6 +60,8 @@ __device__ __forceinline__ void stage_tables(SmemTables* tb, const PoTables* gt)
 #ifndef PO_HAIRPIN_CHUNK
 #define PO_HAIRPIN_CHUNK (1ll << 20)  // hairpins per fill / finish kernel pair: 2 KB of cell values each
 #endif
+// double2 units a hairpin hands from the fill to the finish kernel: CAP cell values + CAP 32-bit cell codes
+#define PO_HAIRPIN_XFER(cap) ((cap) + (cap) / 4)
 #ifndef PO_HAIRPIN32_GROUP
 #define PO_HAIRPIN32_GROUP 8
 #endif
@@ -123,7 +125,7 @@ k_thal(const uint4* __restrict__ A, const uint4* __restrict__ B, long long n, po
                     continue;
                 }
                 thal_hairpin32_warp<PO_HAIRPIN32_GROUP, CAP, PHASE>(*tb, *xt, TA, gt, ws, oa, K, out + item,
-                                                                    cells ? cells + (size_t)(item - first) * CAP : nullptr);
+                                                                    cells ? cells + (size_t)(item - first) * PO_HAIRPIN_XFER(CAP) : nullptr);
             } else {
                 if (ub > CAP) {
                     if (lane == 0) overflow[atomicAdd(overflow_n, 1ull)] = item;
@@ -530,7 +532,7 @@ static int thal_dev(po_ctx* ctx, int type, const void* d_a, const void* d_b, int
             // first tier in two kernels per sub-batch (fill, finish): the cell values cross HBM in between
             const long long chunk = PO_HAIRPIN_CHUNK;
             const long long m0 = n < chunk ? n : chunk;
-            if ((rc = ensure(ctx, ctx->hp_cells, sizeof(double2) * (size_t)PO_HAIRPIN32_CAP * (size_t)m0))) return rc;
+            if ((rc = ensure(ctx, ctx->hp_cells, sizeof(double2) * (size_t)PO_HAIRPIN_XFER(PO_HAIRPIN32_CAP) * (size_t)m0))) return rc;
             double2* cells = (double2*)ctx->hp_cells.p;
             for (long long s = 0; s < n; s += chunk) {
                 const long long m = (n - s) < chunk ? (n - s) : chunk;
@@ -673,7 +675,7 @@ extern "C" int po_score_pairs_batch(po_ctx* ctx, const po_oligo* a, const po_oli
     {
         const long long hm = m0 < (long long)PO_HAIRPIN_CHUNK ? m0 : (long long)PO_HAIRPIN_CHUNK;
         if ((hairpin_a || hairpin_b) &&
-            (rc = ensure(ctx, ctx->hp_cells, sizeof(double2) * (size_t)PO_HAIRPIN32_CAP * (size_t)hm)))
+            (rc = ensure(ctx, ctx->hp_cells, sizeof(double2) * (size_t)PO_HAIRPIN_XFER(PO_HAIRPIN32_CAP) * (size_t)hm)))
             return rc;
     }
     cudaStream_t st = ctx->stream;

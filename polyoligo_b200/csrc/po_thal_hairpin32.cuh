@@ -211,6 +211,17 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
     }
     __syncwarp();
     const int ncell = ws.start[len + 1];
+    // cell codes: built by the fill kernel, which hands them to the finish kernel behind the cell values
+    if constexpr (PHASE == 2) {
+        const uint32_t* codes = reinterpret_cast<const uint32_t*>(cells + CAP);
+        for (int k = lane; k < ncell; k += 32) {
+            ws.code[k] = codes[k];
+            ws.cell[k] = cells[k];
+        }
+        __syncwarp();
+        hairpin_finish<Hairpin32Ws<CAP>, false>(tb, X, A, gt, ws, len, K, r, out, nullptr, 0);
+        return;
+    }
     for (int j = 5; j <= len; ++j) {
         const uint32_t m = HP32_COLM(ws, j);
         if ((m >> lane) & 1u) {  // row i = lane + 1; list order is i descending
@@ -223,12 +234,6 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
         }
     }
     __syncwarp();
-    if constexpr (PHASE == 2) {
-        for (int k = lane; k < ncell; k += 32) ws.cell[k] = cells[k];
-        __syncwarp();
-        hairpin_finish<Hairpin32Ws<CAP>, false>(tb, X, A, gt, ws, len, K, r, out, nullptr, 0);
-        return;
-    }
     for (int k0 = 0; k0 < ncell; k0 += 32) {
         const int k = k0 + lane;
         if (k < ncell) {
@@ -459,7 +464,11 @@ __device__ void thal_hairpin32_warp(const SmemTables& tb, const SmemExtra& X, co
     }
 
     if constexpr (PHASE == 1) {
-        for (int k = lane; k < ncell; k += 32) cells[k] = ws.cell[k];
+        uint32_t* codes = reinterpret_cast<uint32_t*>(cells + CAP);
+        for (int k = lane; k < ncell; k += 32) {
+            cells[k] = ws.cell[k];
+            codes[k] = ws.code[k];
+        }
     } else {
         hairpin_finish<Hairpin32Ws<CAP>, false>(tb, X, A, gt, ws, len, K, r, out, nullptr, 0);
     }
