@@ -151,3 +151,51 @@ def test_offtarget_listing(ref):
     finally:
         ref.lp.set_offtarget_size(0, 1000)
         mine_lp.set_offtarget_size(0, 1000)
+
+
+def test_add_mutations_host_form(ref):
+    # PrimerPair.add_mutations (labels, IUPAC-ambiguous sequences, max_aaf, indel size): the host form
+    # of this package (one pair, no device) against the reference's method on random primers / variants
+    from polyoligo_b200 import lib_primer3 as mine_lp
+    rng = np.random.default_rng(16)
+    for trial in range(150):
+        kasp = bool(rng.integers(0, 2))
+        direction = "R" if rng.integers(0, 2) else "F"
+        fs = int(rng.integers(100, 200))
+        fl, rl = int(rng.integers(18, 26)), int(rng.integers(18, 26))
+        rstop = fs + int(rng.integers(60, 160))
+        spec = {"F": (rand_seq(rng, fl), fs, fs + fl - 1), "R": (rand_seq(rng, rl), rstop - rl + 1, rstop)}
+        if kasp:
+            d = direction
+            spec["A"] = (rand_seq(rng, len(spec[d][0])), spec[d][1], spec[d][2])
+        muts = []
+        for pos in sorted(set(int(p) for p in rng.integers(fs - 5, rstop + 6, 12))):
+            kind = int(rng.integers(0, 4))
+            r0 = rand_seq(rng, 1)
+            if kind == 0:
+                m = dict(ref=r0 + rand_seq(rng, int(rng.integers(1, 4))), alt=[r0])                  # deletion
+            elif kind == 1:
+                m = dict(ref=r0, alt=[r0 + rand_seq(rng, int(rng.integers(1, 70)))])                 # insertion
+            else:
+                m = dict(ref=r0, alt=[rand_seq(rng, 1) for _ in range(int(rng.integers(1, 3)))])     # SNP, 1-2 alleles
+            indel = max(abs(len(m["ref"]) - len(a)) for a in m["alt"])
+            muts.append(types.SimpleNamespace(pos=pos, aaf=float(rng.choice([0.0, 0.013, 0.1, 0.25, 0.5])),
+                                              indel_size=indel, **m))
+
+        def make(mod):
+            pp = mod.PrimerPair()
+            if kasp:
+                pp.primers["A"] = mod.Primer()
+            pp.dir = direction
+            for d, (seq, a, b) in spec.items():
+                pp.primers[d].sequence, pp.primers[d].start, pp.primers[d].stop = seq, a, b
+            return pp
+
+        got, want = make(mine_lp), make(ref.lp)
+        got.add_mutations(muts)
+        want.add_mutations(muts)
+        assert got.max_indel_size == want.max_indel_size
+        for d in spec:
+            g, w = got.primers[d], want.primers[d]
+            assert (g.sequence, g.sequence_ambiguous, list(g.mutations), float(g.max_aaf)) == \
+                   (w.sequence, w.sequence_ambiguous, list(w.mutations), float(w.max_aaf)), (trial, d)
