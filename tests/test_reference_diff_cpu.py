@@ -199,3 +199,121 @@ def test_add_mutations_host_form(ref):
             g, w = got.primers[d], want.primers[d]
             assert (g.sequence, g.sequence_ambiguous, list(g.mutations), float(g.max_aaf)) == \
                    (w.sequence, w.sequence_ambiguous, list(w.mutations), float(w.max_aaf)), (trial, d)
+
+
+def _fill_pairs(rng, mod, pair_cls, n, kasp=False, hrm=False, caps=False):
+    """n primer pairs with every attribute the classify / prune / report code reads, set directly."""
+    pps = []
+    for k in range(n):
+        pp = pair_cls()
+        pp.dir = "R" if rng.integers(0, 2) else "F"
+        start = int(rng.integers(1000, 5000))
+        size = int(rng.integers(60, 400))
+        keys = ["F", "R", "A"] if kasp else ["F", "R"]
+        if kasp and "A" not in pp.primers:
+            pp.primers["A"] = mod.Primer()
+        for d in keys:
+            p = pp.primers[d]
+            ln = int(rng.integers(18, 26))
+            p.sequence = rand_seq(rng, ln)
+            p.sequence_ambiguous = p.sequence[:3] + "R" + p.sequence[4:]
+            p.length = ln
+            p.start, p.stop = (start, start + ln - 1) if d != "R" else (start + size - ln, start + size - 1)
+            p.tm = float(55 + 10 * rng.random())
+            p.gc_content = float(rng.choice([40.0, 45.454545, 52.17391304, 60.0]))
+            p.max_aaf = float(rng.choice([0.0, 0.0, 0.04, 0.13, 0.5]))
+            p.mutations = ["A%dG:0.1" % (p.start + 2)] if rng.integers(0, 3) == 0 else []
+            if kasp:
+                p.reporter = ""
+        pp.product_size = size
+        pp.offtargets = ["chr1:%d-%d" % (start, start + 300)] * int(rng.integers(0, 2))
+        pp.max_indel_size = int(rng.choice([0, 0, 3, 60]))
+        pp.dimer = bool(rng.integers(0, 2))
+        if kasp:
+            pp.ref_dimer, pp.alt_dimer = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        if hrm:
+            pp.hrm = {"delta": round(0.05 * k + 0.013, 3), "ref": 75.1234, "alt": 75.9}   # distinct deltas: no ties
+            pp.seq_x = "ACGTxACGT"
+        if caps:
+            pp.enzymes = [{"name": "EcoRI", "supplier": "BN", "allele": "REF", "fragl": 100 + k, "fragr": 200}]
+            if k % 3 == 0:
+                pp.enzymes.append({"name": "TaqI", "supplier": "X", "allele": "ALT", "fragl": 77, "fragr": 88 + k})
+            pp.seq_x = "ACGTxACGT"
+        pps.append(pp)
+    return pps
+
+
+@pytest.mark.parametrize("assay", ["PCR", "HRM", "CAPS", "KASP"])
+def test_classify_prune_and_report_writers(ref, assay, tmp_path):
+    # classify + prune + print_report on random repositories, files compared byte for byte
+    import importlib
+    from polyoligo_b200 import caps, hrm, kasp, lib_primer3 as mine_lp, pcr
+    ref_mod = importlib.import_module("polyoligo._lib_" + assay.lower())
+    mine_mod = {"PCR": pcr, "HRM": hrm, "CAPS": caps, "KASP": kasp}[assay]
+    for trial in range(12):
+        out = {}
+        for tag, mod, lpm in (("mine", mine_mod, mine_lp), ("ref", ref_mod, ref.lp)):
+            rng = np.random.default_rng(500 + trial)           # the same repository on both sides
+            pair_cls = mod.PrimerPair if assay == "KASP" else lpm.PrimerPair
+            n = int(rng.integers(0, 14)) if trial else 0
+            pps = _fill_pairs(rng, lpm, pair_cls, n, kasp=assay == "KASP", hrm=assay == "HRM", caps=assay == "CAPS")
+            if assay == "PCR":
+                p = lpm.PCR(chrom="chr7", name="reg_%d" % trial)
+            else:
+                p = mod.PCR(snp_id="mk%d" % trial, chrom="chr7", pos=4321, ref="A", alt="" if trial % 2 else "GT")
+            p.pps = pps
+            if assay == "KASP":
+                p.add_reporter_dyes(["GAAGGTCGGAGTCAACGGATT", "GAAGGTGACCAAGTTCATGCT"])
+            p.classify(assay_name=assay)
+            kept = p.prune(5, assay_name="HRM") if assay == "HRM" else p.prune(5)
+            base = str(tmp_path / ("%s_%s_%d" % (tag, assay, trial)))
+            mod.print_report(p, base)
+            mod.print_report_header(base + "_hdr.txt")
+            out[tag] = (int(kept), open(base + ".txt").read(), open(base + ".bed").read(), open(base + "_hdr.txt").read())
+        assert out["mine"] == out["ref"], (assay, trial)
+
+
+def test_get_primers_result_parsing(ref, monkeypatch):
+    # lib_primer3.get_primers' dict -> PrimerPair conversion on random designPrimers-style answers
+    from polyoligo_b200 import lib_primer3 as mine_lp
+    rng = np.random.default_rng(17)
+    for trial in range(60):
+        n = int(rng.integers(0, 12))
+        d = {"PRIMER_LEFT_EXPLAIN": "considered 10", "PRIMER_PAIR_NUM_RETURNED": n, "PRIMER_LEFT_NUM_RETURNED": n}
+        order = list(rng.permutation(n))
+        for i in order:
+            i = int(i)
+            ls, ll, rs, rl = int(rng.integers(0, 200)), int(rng.integers(18, 26)), int(rng.integers(300, 500)), int(rng.integers(18, 26))
+            d["PRIMER_PAIR_%d_PENALTY" % i] = float(rng.random())
+            d["PRIMER_LEFT_%d_SEQUENCE" % i] = rand_seq(rng, ll)
+            d["PRIMER_RIGHT_%d_SEQUENCE" % i] = rand_seq(rng, rl)
+            d["PRIMER_LEFT_%d" % i] = (ls, ll)
+            d["PRIMER_RIGHT_%d" % i] = (rs, rl)
+            for side in ("LEFT", "RIGHT"):
+                for f in ("TM", "GC_PERCENT", "SELF_ANY_TH", "SELF_END_TH", "HAIRPIN_TH", "END_STABILITY", "PENALTY"):
+                    d["PRIMER_%s_%d_%s" % (side, i, f)] = float(rng.random() * 60)
+            d["PRIMER_PAIR_%d_COMPL_ANY_TH" % i] = float(rng.random())
+            d["PRIMER_PAIR_%d_COMPL_END_TH" % i] = float(rng.random())
+            d["PRIMER_PAIR_%d_PRODUCT_SIZE" % i] = rs - ls + 1
+        if trial % 10 == 9:
+            d["PRIMER_WARNING" if trial % 20 == 9 else "PRIMER_ERROR"] = "something"
+        ts = int(rng.integers(1, 10 ** 6))
+        sys.modules["primer3"].bindings.designPrimers = lambda seq_args, _d=d: dict(_d)
+        want = ref.lp.get_primers({"SEQUENCE_TEMPLATE": "ACGT"}, target_start=ts)
+        got = mine_lp.parse_p3_result(dict(d), target_start=ts)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            gd = {k: v for k, v in g.__dict__.items() if k != "primers"}
+            wd = {k: v for k, v in w.__dict__.items() if k != "primers"}
+            for k in wd:                     # every attribute the reference's pair carries
+                if k in ("enzymes", "seq_x"):
+                    continue
+                assert gd[k] == wd[k], (trial, k)
+            for side in "FR":
+                wp = w.primers[side].__dict__
+                gp = g.primers[side].__dict__
+                for k, v in wp.items():
+                    if k in ("is_marker", "marker_pos", "seed"):
+                        continue
+                    assert gp[k] == v, (trial, side, k)
+    sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
