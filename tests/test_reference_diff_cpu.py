@@ -317,3 +317,134 @@ def test_get_primers_result_parsing(ref, monkeypatch):
                         continue
                     assert gp[k] == v, (trial, side, k)
     sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
+
+
+def test_kasp_merge_and_round_robin(ref, monkeypatch):
+    # _lib_kasp.design_primers (merge_primers + the round-robin over the marker primers + dedup + the
+    # validity of the common primer) on random canned picker answers and a canned validity rule
+    import zlib
+    import polyoligo._lib_kasp as ref_kasp
+    from polyoligo_b200 import kasp as mine_kasp, lib_primer3 as mine_lp
+    rng = np.random.default_rng(18)
+
+    def valid_rule(seq):
+        return zlib.crc32(seq.encode()) % 4 != 0
+
+    monkeypatch.setattr(ref.lp.Primer, "is_valid", lambda self: valid_rule(self.sequence))
+    monkeypatch.setattr(mine_lp, "is_valid_batch", lambda primers, device=None: [valid_rule(p.sequence) for p in primers])
+    for trial in range(40):
+        template = rand_seq(rng, 400)
+        roi = types.SimpleNamespace(seq=template, start=int(rng.integers(1, 10 ** 5)), chrom="c")
+        n_mpp = int(rng.integers(1, 7))
+        spec = []
+        for m in range(n_mpp):
+            d = "R" if rng.integers(0, 2) else "F"
+            ln = int(rng.integers(18, 26))
+            spec.append(dict(dir=d, seq=rand_seq(rng, ln), alt=rand_seq(rng, ln), start=roi.start + 200 - ln, stop=roi.start + 199))
+        pool = [rand_seq(rng, int(rng.integers(18, 26))) for _ in range(12)]      # common primers, shared: duplicates occur
+        answers = {}
+        for passno in range(2):
+            for m, sp in enumerate(spec):
+                d = {}
+                for i in range(int(rng.integers(0, 7))):
+                    other = pool[int(rng.integers(0, len(pool)))]
+                    left, right = (sp["seq"], other) if sp["dir"] == "F" else (other, sp["seq"])
+                    d["PRIMER_PAIR_%d_PENALTY" % i] = float(i)
+                    d["PRIMER_LEFT_%d_SEQUENCE" % i] = left
+                    d["PRIMER_RIGHT_%d_SEQUENCE" % i] = right
+                    d["PRIMER_LEFT_%d" % i] = (int(rng.integers(0, 150)), len(left))
+                    d["PRIMER_RIGHT_%d" % i] = (int(rng.integers(250, 399)), len(right))
+                    for side in ("LEFT", "RIGHT"):
+                        for f in ("END_STABILITY", "HAIRPIN_TH", "PENALTY", "SELF_ANY_TH", "SELF_END_TH"):
+                            d["PRIMER_%s_%d_%s" % (side, i, f)] = float(rng.random())
+                    d["PRIMER_PAIR_%d_COMPL_ANY_TH" % i] = 1.0
+                    d["PRIMER_PAIR_%d_COMPL_END_TH" % i] = 2.0
+                    d["PRIMER_PAIR_%d_PRODUCT_SIZE" % i] = 150
+                answers[(passno, m)] = d
+        state = {"pass": 0}
+
+        def find(args):
+            key = "SEQUENCE_PRIMER" if "SEQUENCE_PRIMER" in args else "SEQUENCE_PRIMER_REVCOMP"
+            d = "F" if key == "SEQUENCE_PRIMER" else "R"
+            for m, sp in enumerate(spec):
+                if sp["dir"] == d and sp["seq"] == args[key]:
+                    return dict(answers[(state["pass"], m)])
+            raise AssertionError("unknown marker primer")
+
+        sys.modules["primer3"].bindings.designPrimers = lambda seq_args: find(seq_args)
+        monkeypatch.setattr(mine_lp, "get_primers_batch",
+                            lambda seq_args_list, target_starts, device=None:
+                            [mine_lp.parse_p3_result(find(a), ts) for a, ts in zip(seq_args_list, target_starts)])
+
+        def mpps_of(kmod):
+            out = []
+            for sp in spec:
+                pp = kmod.PrimerPair()
+                pp.dir = sp["dir"]
+                p = pp.primers[sp["dir"]]
+                p.sequence, p.start, p.stop = sp["seq"], sp["start"], sp["stop"]
+                pp.primers["A"].sequence = sp["alt"]
+                out.append(pp)
+            return out
+
+        got, want = [], []
+        for passno, n_primers in ((0, int(rng.integers(1, 12))), (1, int(rng.integers(6, 20)))):
+            state["pass"] = passno
+            got = mine_kasp.design_primers(got, mpps_of(mine_kasp), roi, sequence_excluded_region=[[0, 5]], n_primers=n_primers)
+            want = ref_kasp.design_primers(pps_repo=want, mpps=mpps_of(ref_kasp), roi=roi, sequence_excluded_region=[[0, 5]],
+                                           n_primers=n_primers)
+            rows = lambda repo: [(pp.dir, pp.penalty, pp.product_size) + tuple(
+                (pp.primers[d].sequence, pp.primers[d].start, pp.primers[d].stop, pp.primers[d].id) for d in "FRA") for pp in repo]
+            assert rows(got) == rows(want), (trial, passno)
+    sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
+
+
+def test_pcr_selection_with_max_unique(ref, monkeypatch):
+    # _lib_pcr.design_primers: validity of both primers + the max_unique rule (incl. its counting of rejected
+    # pairs) over several search passes into one repository, on random canned picker answers
+    import zlib
+    import polyoligo._lib_pcr as ref_pcr
+    from polyoligo_b200 import lib_primer3 as mine_lp, pcr as mine_pcr
+    rng = np.random.default_rng(19)
+
+    def valid_rule(seq):
+        return zlib.crc32(seq.encode()) % 5 != 0
+
+    monkeypatch.setattr(ref.lp.Primer, "is_valid", lambda self: valid_rule(self.sequence))
+    monkeypatch.setattr(mine_lp, "is_valid_batch", lambda primers, device=None: [valid_rule(p.sequence) for p in primers])
+    for trial in range(40):
+        lefts = [rand_seq(rng, int(rng.integers(18, 26))) for _ in range(5)]
+        rights = [rand_seq(rng, int(rng.integers(18, 26))) for _ in range(5)]
+        roi = types.SimpleNamespace(seq=rand_seq(rng, 300), chrom="c", left_roi=types.SimpleNamespace(start=int(rng.integers(1, 9999))))
+        answers = []
+        for passno in range(3):
+            d = {}
+            for i in range(int(rng.integers(0, 10))):
+                left, right = lefts[int(rng.integers(0, 5))], rights[int(rng.integers(0, 5))]
+                d["PRIMER_PAIR_%d_PENALTY" % i] = float(i)
+                d["PRIMER_LEFT_%d_SEQUENCE" % i] = left
+                d["PRIMER_RIGHT_%d_SEQUENCE" % i] = right
+                d["PRIMER_LEFT_%d" % i] = (int(rng.integers(0, 100)), len(left))
+                d["PRIMER_RIGHT_%d" % i] = (int(rng.integers(200, 299)), len(right))
+                d["PRIMER_PAIR_%d_PRODUCT_SIZE" % i] = 120
+            if passno == 2 and trial % 7 == 0:
+                d["PRIMER_ERROR"] = "boom"
+            answers.append(d)
+        state = {"pass": 0}
+        sys.modules["primer3"].bindings.designPrimers = lambda seq_args: dict(answers[state["pass"]])
+        monkeypatch.setattr(mine_lp, "get_primers_batch",
+                            lambda seq_args_list, target_starts, device=None:
+                            [mine_lp.parse_p3_result(dict(answers[state["pass"]]), ts) for ts in target_starts])
+        max_unique = [np.inf, 1, 2, 3][trial % 4]
+        n_primers = int(rng.integers(1, 9))
+        got, want = [], []
+        for passno in range(3):
+            state["pass"] = passno
+            got = mine_pcr.design_primers(got, roi, sequence_target=[[100, 50]], sequence_excluded_region=[[0, 3]],
+                                          n_primers=n_primers, max_unique=max_unique)
+            want = ref_pcr.design_primers(pps_repo=want, roi=roi, sequence_target=[[100, 50]], sequence_excluded_region=[[0, 3]],
+                                          n_primers=n_primers, max_unique=max_unique)
+            rows = lambda repo: [(pp.chrom, pp.penalty, pp.product_size) + tuple(
+                (pp.primers[d].sequence, pp.primers[d].start, pp.primers[d].stop, pp.primers[d].id) for d in "FR") for pp in repo]
+            assert rows(got) == rows(want), (trial, passno, max_unique)
+    sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
