@@ -448,3 +448,47 @@ def test_pcr_selection_with_max_unique(ref, monkeypatch):
                 (pp.primers[d].sequence, pp.primers[d].start, pp.primers[d].stop, pp.primers[d].id) for d in "FR") for pp in repo]
             assert rows(got) == rows(want), (trial, passno, max_unique)
     sys.modules["primer3"].bindings.designPrimers = lambda *a, **k: {}
+
+
+def test_will_it_cut_on_the_reference_enzyme_table(ref):
+    # PCRproduct (seq / seq_alt / seq_x) and will_it_cut with every enzyme of the reference's type2.json
+    # (degenerate recognition sites included), shared-enzyme-dict quirk included
+    import polyoligo._lib_caps as ref_caps
+    from polyoligo_b200 import caps as mine_caps, lib_markers as mine_lm
+    rng = np.random.default_rng(20)
+    table = ref_caps.get_enzymes(included_enzymes=None)
+    assert mine_caps.get_enzymes(filename=ref_caps.ENZYME_FILENAME) == table
+    assert [e["name"] for e in mine_caps.get_enzymes(["EcoRI", "TaqI"], ref_caps.ENZYME_FILENAME)] == \
+           [e["name"] for e in ref_caps.get_enzymes(included_enzymes=["EcoRI", "TaqI"])]
+    genome = rand_seq(rng, 3000)
+
+    class Fetch:
+        def fetch(self, query):
+            q = query[0]
+            return {"%s:%d-%d" % (q["chr"], q["start"], q["stop"]): genome[q["start"] - 1:q["stop"]]}
+
+    for trial in range(25):
+        pos1 = int(rng.integers(800, 2200))
+        refa = genome[pos1 - 1:pos1 - 1 + int(rng.choice([1, 1, 1, 2]))]
+        alt = rand_seq(rng, int(rng.choice([1, 1, 2, 3])))
+        while alt == refa:
+            alt = rand_seq(rng, len(alt))
+        marker = types.SimpleNamespace(name="m%d" % trial, chrom="c", pos1=pos1, ref=refa, alt=alt, n=len(refa))
+        mine_enz, ref_enz = [dict(e) for e in table], [dict(e) for e in table]
+        for k in range(6):                                   # several products share one enzyme list (the quirk)
+            fstart = pos1 - int(rng.integers(30, 400))
+            rstop = pos1 + int(rng.integers(30, 400))
+            pp = types.SimpleNamespace(primers={"F": types.SimpleNamespace(start=fstart), "R": types.SimpleNamespace(stop=rstop)})
+            roi = types.SimpleNamespace(chrom="c", blast_hook=Fetch(), malign_hook=None, vcf_hook=None, marker=marker,
+                                        do_print_alt_subjects=False)
+            got, want = mine_lm.PCRproduct(roi=roi, pp=pp), ref.lm.PCRproduct(roi=roi, pp=pp)
+            assert (got.roi.seq, got.roi.seq_alt, got.roi.seq_x, got.roi.n) == \
+                   (want.roi.seq, want.roi.seq_alt, want.roi.seq_x, want.roi.n)
+            mfs = int(rng.choice([0, 20, 60]))
+            got.will_it_cut(mine_enz, mfs)
+            want.will_it_cut(enzymes=ref_enz, min_fragment_size=mfs)
+            assert [(e["name"], e["allele"], float(e["fragl"]), float(e["fragr"])) for e in got.enzymes] == \
+                   [(e["name"], e["allele"], float(e["fragl"]), float(e["fragr"])) for e in want.enzymes], (trial, k)
+        # the shared dicts ended up with the same last-writer values
+        key = lambda e: (e["name"], e.get("allele"), None if "fragl" not in e else float(e["fragl"]))
+        assert [key(e) for e in mine_enz] == [key(e) for e in ref_enz]
