@@ -87,6 +87,43 @@ def golden_marker_primers(rng):
     dump("kasp_marker_primers.json", {"globals": KASP_GLOBALS, "tm_delta": 5.0, "cases": cases})
 
 
+def golden_marker_primers_edges(rng):
+    """a3 again, away from the centre of the template: markers next to either template end (Python's
+    negative-index slices come into play), longer indels, templates of other lengths."""
+    lp.set_tm_delta(5.0)
+    lp.PRIMER3_GLOBALS.clear()
+    lp.PRIMER3_GLOBALS.update(KASP_GLOBALS)
+    cases = []
+    specs = []
+    for idx in (0, 3, 17, 18, 24, 25, 26, 40):
+        specs += [(500, idx, 1, 1), (500, 499 - idx, 1, 1)]
+    specs += [(500, 20, 4, 1), (500, 22, 1, 5), (500, 478, 6, 2), (500, 470, 2, 9), (500, 249, 10, 1), (500, 249, 1, 12),
+              (120, 60, 1, 1), (120, 30, 3, 1), (61, 30, 1, 1), (300, 290, 2, 2), (512, 256, 1, 1), (512, 500, 1, 3)]
+    for n, idx, rl, al in specs:
+        seq = rand_seq(rng, n, gc=rng.choice([0.42, 0.5, 0.58]))
+        start = int(rng.integers(1000, 100000))
+        rl = min(rl, n - idx)
+        ref = seq[idx:idx + rl]
+        alt = ref
+        while alt == ref:
+            alt = rand_seq(rng, al)
+        hroi = make_hroi(seq, start, start + idx, ref, alt)
+        real_valid = lp.Primer.is_valid
+        lp.Primer.is_valid = lambda self: True
+        try:
+            allc = lk.get_marker_primers(hroi)
+        finally:
+            lp.Primer.is_valid = real_valid
+        kept = lk.get_marker_primers(hroi)
+        cases.append({
+            "seq": seq, "start": start, "stop": hroi.stop, "pos1": hroi.marker.pos1, "ref": ref, "alt": alt,
+            "all": [{"dir": pp.dir, "ref": pp.primers[pp.dir].sequence, "alt": pp.primers["A"].sequence}
+                    for pp in allc],
+            "kept": [{"dir": pp.dir, "ref": pp.primers[pp.dir].sequence, "alt": pp.primers["A"].sequence,
+                      "tm_ref": pp.primers[pp.dir].tm, "tm_alt": pp.primers["A"].tm} for pp in kept]})
+    dump("kasp_marker_primers_edges.json", {"globals": KASP_GLOBALS, "tm_delta": 5.0, "cases": cases})
+
+
 def golden_is_valid(rng):
     """a1/a2: Primer.calc_thermals / is_valid (reference lib_primer3.py:56-97)."""
     lp.PRIMER3_GLOBALS.clear()
@@ -702,6 +739,9 @@ if __name__ == "__main__":
     if "--design-only" in sys.argv:
         golden_design(np.random.default_rng(20240610))
         sys.exit(0)
+    if "--edges-only" in sys.argv:
+        golden_marker_primers_edges(np.random.default_rng(20240614))
+        sys.exit(0)
     if "--lib-markers-only" in sys.argv:
         golden_lib_markers(np.random.default_rng(20240613))
         sys.exit(0)
@@ -719,3 +759,4 @@ if __name__ == "__main__":
     golden_offtargets(np.random.default_rng(20240611))
     golden_pcr_main(np.random.default_rng(20240612))
     golden_lib_markers(np.random.default_rng(20240613))
+    golden_marker_primers_edges(np.random.default_rng(20240614))
